@@ -1,0 +1,387 @@
+// host_api.cu -- HOST-buffer entry points (what `require 'libvolstn'` binds for torch.FloatTensor /
+// torch.DoubleTensor in the reference, stn3dtorch/init.c:13-21).
+//
+// There is no CPU compute path: host tensors are cut into batch slices (samples are independent:
+// batch is the outermost loop of every reference function, ...c:482,641) and each slice is
+// H2D-copied, processed by the sm_100a kernels and D2H-copied on one of kSlots streams, so that the
+// upload of slice i+1, the kernels of slice i and the download of slice i-1 overlap (the B200 has
+// independent copy engines per direction).  The call returns after the last download.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "volstn_common.cuh"
+#include "volstn_internal.h"
+
+struct volstn_host_ctx {
+  static constexpr int kSlots = 3;
+  int device;
+  cudaStream_t stream[kSlots];
+  void *arena[kSlots];
+  size_t cap[kSlots];
+};
+
+namespace volstn {
+namespace {
+
+constexpr size_t kAlign = 256;
+constexpr size_t kSliceTargetBytes = 48u << 20;  // per slice, all tensors together
+
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ensure_arena(volstn_host_ctx *c, int slot, size_t bytes) {
+  if (c->cap[slot] >= bytes) return VOLSTN_OK;
+  VOLSTN_CUDA_TRY(cudaStreamSynchronize(c->stream[slot]));
+  if (c->arena[slot]) VOLSTN_CUDA_TRY(cudaFree(c->arena[slot]));
+  c->arena[slot] = nullptr;
+  c->cap[slot] = 0;
+  VOLSTN_CUDA_TRY(cudaMalloc(&c->arena[slot], bytes));
+  c->cap[slot] = bytes;
+  return VOLSTN_OK;
+}
+
+int sync_all(volstn_host_ctx *c) {
+  int rc = VOLSTN_OK;
+  for (int s = 0; s < volstn_host_ctx::kSlots; s++) {
+    cudaError_t e = cudaStreamSynchronize(c->stream[s]);
+    if (e != cudaSuccess && rc == VOLSTN_OK) rc = cuda_fail(e);
+  }
+  return rc;
+}
+
+// samples per slice: ~kSliceTargetBytes, and enough slices to keep all slots busy
+int64_t slice_batch(int64_t B, size_t bytes_per_sample) {
+  int64_t bs = (int64_t)(kSliceTargetBytes / (bytes_per_sample ? bytes_per_sample : 1));
+  const int64_t per_slot = (B + volstn_host_ctx::kSlots - 1) / volstn_host_ctx::kSlots;
+  bs = std::min(bs, per_slot);
+  return std::max<int64_t>(bs, 1);
+}
+
+// a contiguous B-slice of a contiguous 5-D host tensor, re-homed at `dev`
+volstn_tensor5 slice_desc(const volstn_tensor5 *t, int64_t b0, int64_t nb, void *dev) {
+  volstn_tensor5 d = *t;
+  d.data = dev;
+  d.size[0] = nb;
+  (void)b0;
+  return d;
+}
+
+size_t sample_elems(const volstn_tensor5 *t) { return (size_t)(t->size[1] * t->size[2] * t->size[3] * t->size[4]); }
+
+}  // namespace
+}  // namespace volstn
+
+using namespace volstn;
+
+extern "C" {
+
+int volstn_b200_host_ctx_create(int device, volstn_host_ctx **out) {
+  if (!out) return VOLSTN_ERR_ARG;
+  *out = nullptr;
+  int rc = volstn_b200_device_check(device);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  volstn_host_ctx *c = new (std::nothrow) volstn_host_ctx();
+  if (!c) return VOLSTN_ERR_ARG;
+  c->device = device;
+  for (int s = 0; s < volstn_host_ctx::kSlots; s++) {
+    c->arena[s] = nullptr;
+    c->cap[s] = 0;
+    c->stream[s] = nullptr;
+  }
+  for (int s = 0; s < volstn_host_ctx::kSlots; s++) {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      volstn_b200_host_ctx_destroy(c);
+      return cuda_fail(e);
+    }
+  }
+  *out = c;
+  return VOLSTN_OK;
+}
+
+int volstn_b200_host_ctx_destroy(volstn_host_ctx *c) {
+  if (!c) return VOLSTN_OK;
+  DeviceGuard g(c->device);
+  for (int s = 0; s < volstn_host_ctx::kSlots; s++) {
+    if (c->stream[s]) {
+      cudaStreamSynchronize(c->stream[s]);
+      cudaStreamDestroy(c->stream[s]);
+    }
+    if (c->arena[s]) cudaFree(c->arena[s]);
+  }
+  delete c;
+  return VOLSTN_OK;
+}
+
+int volstn_b200_host_pin(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return VOLSTN_ERR_ARG;
+  VOLSTN_CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return VOLSTN_OK;
+}
+
+int volstn_b200_host_unpin(void *ptr) {
+  if (!ptr) return VOLSTN_ERR_ARG;
+  VOLSTN_CUDA_TRY(cudaHostUnregister(ptr));
+  return VOLSTN_OK;
+}
+
+int volstn_b200_host_sampler_forward(volstn_host_ctx *c, int dtype, int G, const volstn_tensor5 *vol,
+                                     const volstn_tensor5 *grid, const volstn_tensor5 *out, unsigned flags) {
+  if (!c || !vol || !grid || !out) return VOLSTN_ERR_ARG;
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  if (!desc_contiguous(vol) || !desc_contiguous(grid) || !desc_contiguous(out)) return VOLSTN_ERR_LAYOUT;
+  if (grid->size[0] != vol->size[0] || out->size[0] != vol->size[0]) return VOLSTN_ERR_SHAPE;
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  const int64_t B = vol->size[0];
+  if (B == 0 || desc_numel(out) == 0) {
+    // still validate shapes through the device entry point (no launch happens for empty outputs)
+    return sampler_forward_impl(dtype, G, vol, grid, out, flags, nullptr);
+  }
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t nv = sample_elems(vol) * esz, ng = sample_elems(grid) * esz, no = sample_elems(out) * esz;
+  const int64_t bs = slice_batch(B, nv + ng + no);
+  const size_t need = align_up(nv * bs) + align_up(ng * bs) + align_up(no * bs);
+  int rc = VOLSTN_OK;
+  int slice = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
+    const int64_t nb = std::min(bs, B - b0);
+    const int s = slice % volstn_host_ctx::kSlots;
+    if ((rc = ensure_arena(c, s, need))) break;
+    char *dv = static_cast<char *>(c->arena[s]);
+    char *dg = dv + align_up(nv * bs);
+    char *dout = dg + align_up(ng * bs);
+    cudaStream_t st = c->stream[s];
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dv, static_cast<const char *>(vol->data) + b0 * nv, nb * nv, cudaMemcpyHostToDevice, st)) !=
+            cudaSuccess ||
+        (e = cudaMemcpyAsync(dg, static_cast<const char *>(grid->data) + b0 * ng, nb * ng, cudaMemcpyHostToDevice, st)) !=
+            cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+    volstn_tensor5 tv = slice_desc(vol, b0, nb, dv), tg = slice_desc(grid, b0, nb, dg), to = slice_desc(out, b0, nb, dout);
+    if ((rc = sampler_forward_impl(dtype, G, &tv, &tg, &to, flags, st))) break;
+    if ((e = cudaMemcpyAsync(static_cast<char *>(out->data) + b0 * no, dout, nb * no, cudaMemcpyDeviceToHost, st)) !=
+        cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+  }
+  const int rs = sync_all(c);
+  return rc ? rc : rs;
+}
+
+int volstn_b200_host_sampler_backward(volstn_host_ctx *c, int dtype, int G, const volstn_tensor5 *vol,
+                                      const volstn_tensor5 *grid, const volstn_tensor5 *gradVol,
+                                      const volstn_tensor5 *gradGrid, const volstn_tensor5 *gradOut,
+                                      unsigned flags) {
+  if (!c || !vol || !grid || !gradOut) return VOLSTN_ERR_ARG;
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID, ov = flags & VOLSTN_BWD_ONLY_VOLUME;
+  if ((og && ov) || (!og && !gradVol) || (!ov && !gradGrid)) return VOLSTN_ERR_ARG;
+  if (!desc_contiguous(vol) || !desc_contiguous(grid) || !desc_contiguous(gradOut)) return VOLSTN_ERR_LAYOUT;
+  if (!og && !desc_contiguous(gradVol)) return VOLSTN_ERR_LAYOUT;
+  if (!ov && !desc_contiguous(gradGrid)) return VOLSTN_ERR_LAYOUT;
+  if (grid->size[0] != vol->size[0] || gradOut->size[0] != vol->size[0]) return VOLSTN_ERR_SHAPE;
+  if (!og && gradVol->size[0] != vol->size[0]) return VOLSTN_ERR_SHAPE;
+  if (!ov && gradGrid->size[0] != vol->size[0]) return VOLSTN_ERR_SHAPE;
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  const int64_t B = vol->size[0];
+  if (B == 0 || desc_numel(gradOut) == 0) {
+    if (!og && (flags & VOLSTN_BWD_ZERO_GRADVOL) && desc_numel(gradVol))
+      memset(gradVol->data, 0, (size_t)desc_numel(gradVol) * esz);  // host zero-fill: data movement, not compute
+    return sampler_backward_impl(dtype, G, vol, grid, gradVol, gradGrid, gradOut, flags & ~VOLSTN_BWD_ZERO_GRADVOL,
+                                 nullptr);
+  }
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t nv = sample_elems(vol) * esz, ng = sample_elems(grid) * esz, no = sample_elems(gradOut) * esz;
+  const size_t ngv = og ? 0 : nv, ngg = ov ? 0 : ng;
+  const int64_t bs = slice_batch(B, nv + ng + no + ngv + ngg);
+  const size_t need =
+      align_up(nv * bs) + align_up(ng * bs) + align_up(no * bs) + align_up(ngv * bs) + align_up(ngg * bs);
+  const bool upload_gv = !og && !(flags & VOLSTN_BWD_ZERO_GRADVOL);  // accumulate semantics of the reference
+  int rc = VOLSTN_OK;
+  int slice = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
+    const int64_t nb = std::min(bs, B - b0);
+    const int s = slice % volstn_host_ctx::kSlots;
+    if ((rc = ensure_arena(c, s, need))) break;
+    char *dv = static_cast<char *>(c->arena[s]);
+    char *dg = dv + align_up(nv * bs);
+    char *dgo = dg + align_up(ng * bs);
+    char *dgv = dgo + align_up(no * bs);
+    char *dgg = dgv + align_up(ngv * bs);
+    cudaStream_t st = c->stream[s];
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](char *dst, const volstn_tensor5 *t, size_t per) {
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dst, static_cast<const char *>(t->data) + b0 * per, nb * per, cudaMemcpyHostToDevice, st);
+    };
+    h2d(dv, vol, nv);
+    h2d(dg, grid, ng);
+    h2d(dgo, gradOut, no);
+    if (upload_gv) h2d(dgv, gradVol, nv);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+    volstn_tensor5 tv = slice_desc(vol, b0, nb, dv), tg = slice_desc(grid, b0, nb, dg),
+                   tgo = slice_desc(gradOut, b0, nb, dgo);
+    volstn_tensor5 tgv, tgg;
+    if (!og) tgv = slice_desc(gradVol, b0, nb, dgv);
+    if (!ov) tgg = slice_desc(gradGrid, b0, nb, dgg);
+    if ((rc = sampler_backward_impl(dtype, G, &tv, &tg, og ? nullptr : &tgv, ov ? nullptr : &tgg, &tgo, flags, st)))
+      break;
+    auto d2h = [&](const volstn_tensor5 *t, const char *src, size_t per) {
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(static_cast<char *>(t->data) + b0 * per, src, nb * per, cudaMemcpyDeviceToHost, st);
+    };
+    if (!og) d2h(gradVol, dgv, nv);
+    if (!ov) d2h(gradGrid, dgg, ng);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+  }
+  const int rs = sync_all(c);
+  return rc ? rc : rs;
+}
+
+int volstn_b200_host_gridgen_forward(volstn_host_ctx *c, int dtype, const void *T, void *out, int64_t B, int64_t D,
+                                     int64_t H, int64_t W) {
+  if (!c) return VOLSTN_ERR_ARG;
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  if (B < 0 || D < 2 || H < 2 || W < 2) return VOLSTN_ERR_SHAPE;
+  if (B == 0) return VOLSTN_OK;
+  if (!T || !out) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  const size_t nt = 16 * esz, no = (size_t)(D * H * W * 4) * esz;
+  const int64_t bs = slice_batch(B, nt + no);
+  const size_t need = align_up(nt * bs) + align_up(no * bs);
+  int rc = VOLSTN_OK;
+  int slice = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
+    const int64_t nb = std::min(bs, B - b0);
+    const int s = slice % volstn_host_ctx::kSlots;
+    if ((rc = ensure_arena(c, s, need))) break;
+    char *dt = static_cast<char *>(c->arena[s]);
+    char *dout = dt + align_up(nt * bs);
+    cudaStream_t st = c->stream[s];
+    cudaError_t e = cudaMemcpyAsync(dt, static_cast<const char *>(T) + b0 * nt, nb * nt, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+    if ((rc = volstn_b200_gridgen_forward(dtype, dt, dout, nb, D, H, W, st))) break;
+    e = cudaMemcpyAsync(static_cast<char *>(out) + b0 * no, dout, nb * no, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+  }
+  const int rs = sync_all(c);
+  return rc ? rc : rs;
+}
+
+int volstn_b200_host_gridgen_backward(volstn_host_ctx *c, int dtype, const void *gradGrid, void *gradT, int64_t B,
+                                      int64_t D, int64_t H, int64_t W) {
+  if (!c) return VOLSTN_ERR_ARG;
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  if (B < 0 || D < 2 || H < 2 || W < 2) return VOLSTN_ERR_SHAPE;
+  if (B == 0) return VOLSTN_OK;
+  if (!gradGrid || !gradT) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  const size_t nt = 16 * esz, ng = (size_t)(D * H * W * 4) * esz;
+  const int64_t bs = slice_batch(B, nt + ng);
+  const size_t ws = volstn_b200_gridgen_backward_workspace(bs, D, H, W);
+  const size_t need = align_up(ng * bs) + align_up(nt * bs) + align_up(ws);
+  int rc = VOLSTN_OK;
+  int slice = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
+    const int64_t nb = std::min(bs, B - b0);
+    const int s = slice % volstn_host_ctx::kSlots;
+    if ((rc = ensure_arena(c, s, need))) break;
+    char *dg = static_cast<char *>(c->arena[s]);
+    char *dt = dg + align_up(ng * bs);
+    char *dws = dt + align_up(nt * bs);
+    cudaStream_t st = c->stream[s];
+    cudaError_t e =
+        cudaMemcpyAsync(dg, static_cast<const char *>(gradGrid) + b0 * ng, nb * ng, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+    // workspace sized for `bs` samples is large enough for the (possibly shorter) last slice
+    if ((rc = volstn_b200_gridgen_backward(dtype, dg, dt, nb, D, H, W, dws,
+                                           std::max(ws, volstn_b200_gridgen_backward_workspace(nb, D, H, W)), st)))
+      break;
+    e = cudaMemcpyAsync(static_cast<char *>(gradT) + b0 * nt, dt, nb * nt, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+  }
+  const int rs = sync_all(c);
+  return rc ? rc : rs;
+}
+
+static int host_cumsum(volstn_host_ctx *c, int dtype, const void *in, void *out, int64_t B, int N,
+                       const int64_t *dims, bool reverse) {
+  if (!c || !dims || N < 1) return VOLSTN_ERR_ARG;
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  int64_t S = 1;
+  for (int i = 0; i < N; i++) {
+    if (dims[i] < 0) return VOLSTN_ERR_ARG;
+    S *= dims[i];
+  }
+  if (B <= 0 || S == 0) return B < 0 ? VOLSTN_ERR_ARG : VOLSTN_OK;
+  if (!in || !out) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  const size_t bytes = (size_t)(B * N * S) * esz;
+  int rc = ensure_arena(c, 0, align_up(bytes) * 2);
+  if (rc) return rc;
+  char *din = static_cast<char *>(c->arena[0]);
+  char *dout = din + align_up(bytes);
+  cudaStream_t st = c->stream[0];
+  VOLSTN_CUDA_TRY(cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, st));
+  rc = reverse ? volstn_b200_cumsum_backward(dtype, din, dout, B, N, dims, st)
+               : volstn_b200_cumsum_forward(dtype, din, dout, B, N, dims, st);
+  if (rc) return rc;
+  VOLSTN_CUDA_TRY(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
+  VOLSTN_CUDA_TRY(cudaStreamSynchronize(st));
+  return VOLSTN_OK;
+}
+
+int volstn_b200_host_cumsum_forward(volstn_host_ctx *c, int dtype, const void *in, void *out, int64_t B, int N,
+                                    const int64_t *dims) {
+  return host_cumsum(c, dtype, in, out, B, N, dims, false);
+}
+
+int volstn_b200_host_cumsum_backward(volstn_host_ctx *c, int dtype, const void *gradOut, void *gradIn, int64_t B,
+                                     int N, const int64_t *dims) {
+  return host_cumsum(c, dtype, gradOut, gradIn, B, N, dims, true);
+}
+
+}  // extern "C"

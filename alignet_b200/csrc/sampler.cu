@@ -1,0 +1,649 @@
+// sampler.cu -- nn.BilinearSamplerVolumetric on sm_100a: forward gather, backward
+// (gradVol scatter-add + gradGrid), index dump, and the C-ABI dispatchers for DEVICE pointers.
+//
+// Replaces stn3dtorch/generic/BilinearSamplerVolumetric.c (CPU) and
+// stn3dtorch/BilinearSamplerVolumetric.cu (the sm_20-era CUDA kernels) -- see include/volstn_b200.h.
+//
+// Thread mapping (the opposite of the reference's warp-per-voxel / lanes-over-channels,
+// ...cu:590,669): one thread per output voxel, consecutive lanes along W, so that
+//   - the grid element is ONE aligned 128-bit streaming load per voxel (G = 4),
+//   - the C output / gradOut channels are one 4C-byte vector access,
+//   - gradGrid is one 128-bit streaming store,
+//   - the eight corner gathers of a warp fall on four short runs of volume rows (L1-resident for
+//     coherent fields), and gradVol reductions are vector `red.global.add` (C = 2, 4).
+#include "sampler.cuh"
+
+namespace volstn {
+
+constexpr int kThreads = 256;
+
+// =============================================================================================
+// per-voxel bodies (packed layout: everything contiguous, 32-bit in-sample offsets)
+// =============================================================================================
+template <typename real, int CT, int G>
+__device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
+                                                     const real *__restrict__ vb, int sD, int sH, int sW,
+                                                     real *__restrict__ o) {
+  using E = Ex<real>;
+  real cw[8];
+  s.corner_weights(cw);
+  const int base = s.base32(sD, sH, sW);
+  if constexpr (CT > 0) {
+    real v[8][CT];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+      for (int t = 0; t < CT; t++) v[k][t] = real(0);  // out-of-bounds corners read as 0 (...c:531-564)
+      if (s.in(k)) {
+        const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
+        ld_channels<real, CT>(vb + off, v[k]);
+      }
+    }
+    real acc[CT];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = (G == 4) ? order_xyz(j) : order_zxy(j);  // ...c:566-573 / ...c:149-156
+#pragma unroll
+      for (int t = 0; t < CT; t++) {
+        const real term = E::mul(cw[k], v[k][t]);
+        acc[t] = (j == 0) ? term : E::add(acc[t], term);
+      }
+    }
+    st_channels_stream<real, CT>(o, acc);
+  } else {
+    int off[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) off[k] = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
+    for (int t = 0; t < a.C; t++) {
+      real acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = (G == 4) ? order_xyz(j) : order_zxy(j);
+        const real v = s.in(k) ? __ldg(vb + off[k] + t) : real(0);
+        const real term = E::mul(cw[k], v);
+        acc = (j == 0) ? term : E::add(acc, term);
+      }
+      o[t] = acc;
+    }
+  }
+}
+
+template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL>
+__device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
+                                                      const real *__restrict__ vb, real *__restrict__ gvb, int sD,
+                                                      int sH, int sW, const real *__restrict__ gop,
+                                                      real *__restrict__ ggp) {
+  using E = Ex<real>;
+  real cw[8];
+  if constexpr (!ONLY_GRID) s.corner_weights(cw);
+  const int base = s.base32(sD, sH, sW);
+  real dot[8];
+  if constexpr (CT > 0) {
+    real go[CT];
+    ld_channels_stream<real, CT>(gop, go);
+    real v[8][CT];
+    if constexpr (!ONLY_VOL) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+#pragma unroll
+        for (int t = 0; t < CT; t++) v[k][t] = real(0);
+        if (s.in(k)) {
+          const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
+          ld_channels<real, CT>(vb + off, v[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
+      if constexpr (!ONLY_VOL) {
+        real d = real(0);  // dot += v * go, channel by channel (...c:736)
+#pragma unroll
+        for (int t = 0; t < CT; t++) d = E::add(d, E::mul(v[k][t], go[t]));
+        dot[k] = s.in(k) ? d : real(0);
+      }
+      if constexpr (!ONLY_GRID) {
+        if (s.in(k)) {
+          real r[CT];
+#pragma unroll
+          for (int t = 0; t < CT; t++) r[t] = E::mul(cw[k], go[t]);  // ...c:737
+          red_channels<real, CT>(gvb + off, r);
+        }
+      }
+    }
+  } else {
+    int off[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      off[k] = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
+      dot[k] = real(0);
+    }
+    for (int t = 0; t < a.C; t++) {
+      const real go = __ldg(gop + t);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (s.in(k)) {
+          if constexpr (!ONLY_VOL) dot[k] = E::add(dot[k], E::mul(__ldg(vb + off[k] + t), go));
+          if constexpr (!ONLY_GRID) red_add(gvb + off[k] + t, E::mul(cw[k], go));
+        }
+      }
+    }
+  }
+  if constexpr (!ONLY_VOL) {
+    real gz, gy, gx;
+    grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
+    st_grad_grid<real, G>(ggp, gz, gy, gx);
+  }
+}
+
+// =============================================================================================
+// packed kernels: grid.x covers the voxels of one sample (VPT per thread, stride kThreads so every
+// access instruction of a warp is contiguous), grid.y walks the batch.
+// =============================================================================================
+template <typename real, int CT, int G, int VPT>
+__global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerArgs<real> a) {
+  const int C = CT ? CT : a.C;
+  const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
+  const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
+  for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
+    const real *vb = a.vol + (long long)b * a.vs[0];
+    const real *gb = a.grid + (long long)b * a.n * G;
+    real *ob = a.out + (long long)b * a.n * C;
+    real zf[VPT], yf[VPT], xf[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+      const long long j = j0 + v * kThreads;
+      if (j < a.n) ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+      const long long j = j0 + v * kThreads;
+      if (j < a.n) {
+        VoxelSetup<real> s;
+        s.init(zf[v], yf[v], xf[v], a);
+        voxel_forward_packed<real, CT, G>(a, s, vb, sD, sH, sW, ob + j * C);
+      }
+    }
+  }
+}
+
+template <typename real, int CT, int G, int VPT, bool ONLY_GRID, bool ONLY_VOL>
+__global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerArgs<real> a) {
+  const int C = CT ? CT : a.C;
+  const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
+  const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
+  for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
+    const real *vb = a.vol + (long long)b * a.vs[0];
+    real *gvb = a.gvol + (long long)b * a.gvs[0];
+    const real *gb = a.grid + (long long)b * a.n * G;
+    real *ggb = a.ggrid + (long long)b * a.n * G;
+    const real *gob = a.gout + (long long)b * a.n * C;
+    real zf[VPT], yf[VPT], xf[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+      const long long j = j0 + v * kThreads;
+      if (j < a.n) ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+      const long long j = j0 + v * kThreads;
+      if (j < a.n) {
+        VoxelSetup<real> s;
+        s.init(zf[v], yf[v], xf[v], a);
+        voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + j * C,
+                                                                 ggb + j * G);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// generic kernels: arbitrary element strides on dims 0..3 of every tensor (the CPU reference
+// honours them, ...c:460-473), any C, float or double, 64-bit offsets.  One thread per voxel.
+// =============================================================================================
+template <typename real>
+__device__ __forceinline__ long long voxel_offset(long long idx, const SamplerArgs<real> &a, const long long (&st)[4],
+                                                  int &b) {
+  const long long x = idx % a.oW;
+  long long r = idx / a.oW;
+  const long long y = r % a.oH;
+  r /= a.oH;
+  const long long z = r % a.oD;
+  b = (int)(r / a.oD);
+  return (long long)b * st[0] + z * st[1] + y * st[2] + x * st[3];
+}
+
+template <typename real, int G>
+__global__ void __launch_bounds__(kThreads) k_sampler_fwd_generic(const SamplerArgs<real> a) {
+  using E = Ex<real>;
+  const long long total = a.n * a.B;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    int b;
+    const long long goff = voxel_offset<real>(idx, a, a.gs, b);
+    int b2;
+    const long long ooff = voxel_offset<real>(idx, a, a.os, b2);
+    const real *g = a.grid + goff;
+    VoxelSetup<real> s;
+    s.init(g[0], g[1], g[2], a);
+    real cw[8];
+    s.corner_weights(cw);
+    const real *vb = a.vol + (long long)b * a.vs[0];
+    const long long base = s.base64(a.vs[1], a.vs[2], a.vs[3]);
+    long long off[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      off[k] = base + ((k & 1) ? a.vs[3] : 0) + ((k & 2) ? a.vs[2] : 0) + ((k & 4) ? a.vs[1] : 0);
+    real *o = a.out + ooff;
+    for (int t = 0; t < a.C; t++) {
+      real acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = (G == 4) ? order_xyz(j) : order_zxy(j);
+        const real v = s.in(k) ? vb[off[k] + t] : real(0);
+        const real term = E::mul(cw[k], v);
+        acc = (j == 0) ? term : E::add(acc, term);
+      }
+      o[t] = acc;
+    }
+  }
+}
+
+template <typename real, int G, bool ONLY_GRID, bool ONLY_VOL>
+__global__ void __launch_bounds__(kThreads) k_sampler_bwd_generic(const SamplerArgs<real> a) {
+  using E = Ex<real>;
+  const long long total = a.n * a.B;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    int b, bx;
+    const long long goff = voxel_offset<real>(idx, a, a.gs, b);
+    const long long ooff = voxel_offset<real>(idx, a, a.os, bx);
+    const long long ggoff = voxel_offset<real>(idx, a, a.ggs, bx);
+    const real *g = a.grid + goff;
+    VoxelSetup<real> s;
+    s.init(g[0], g[1], g[2], a);
+    real cw[8];
+    s.corner_weights(cw);
+    const real *vb = a.vol + (long long)b * a.vs[0];
+    real *gvb = a.gvol + (long long)b * a.gvs[0];
+    const long long base = s.base64(a.vs[1], a.vs[2], a.vs[3]);
+    const long long gbase = s.base64(a.gvs[1], a.gvs[2], a.gvs[3]);  // gradVol has its own strides (...c:686)
+    real dot[8];
+    long long off[8], goffs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      off[k] = base + ((k & 1) ? a.vs[3] : 0) + ((k & 2) ? a.vs[2] : 0) + ((k & 4) ? a.vs[1] : 0);
+      goffs[k] = gbase + ((k & 1) ? a.gvs[3] : 0) + ((k & 2) ? a.gvs[2] : 0) + ((k & 4) ? a.gvs[1] : 0);
+      dot[k] = real(0);
+    }
+    const real *gop = a.gout + ooff;
+    for (int t = 0; t < a.C; t++) {
+      const real go = gop[t];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (s.in(k)) {
+          if constexpr (!ONLY_VOL) dot[k] = E::add(dot[k], E::mul(vb[off[k] + t], go));
+          if constexpr (!ONLY_GRID) red_add(gvb + goffs[k] + t, E::mul(cw[k], go));
+        }
+      }
+    }
+    if constexpr (!ONLY_VOL) {
+      real gz, gy, gx;
+      grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
+      real *gg = a.ggrid + ggoff;
+      gg[0] = gz;
+      gg[1] = gy;
+      gg[2] = gx;
+      if constexpr (G == 4) gg[3] = real(0);
+    }
+  }
+}
+
+// index / mask dump (debug; bit-exact parity test)
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_sampler_indices(const SamplerArgs<real> a, int32_t *idx_out,
+                                                              uint8_t *mask_out) {
+  const long long total = a.n * a.B;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    int b;
+    const real *g = a.grid + voxel_offset<real>(idx, a, a.gs, b);
+    VoxelSetup<real> s;
+    s.init(g[0], g[1], g[2], a);
+    idx_out[idx * 3 + 0] = s.z0;
+    idx_out[idx * 3 + 1] = s.y0;
+    idx_out[idx * 3 + 2] = s.x0;
+    mask_out[idx] = (uint8_t)s.mask;
+  }
+}
+
+// =============================================================================================
+// host-side validation and dispatch
+// =============================================================================================
+namespace {
+
+bool is_contiguous(const volstn_tensor5 *t) {
+  int64_t expect = 1;
+  for (int i = 4; i >= 0; i--) {
+    if (t->size[i] != 1 && t->stride[i] != expect) return false;
+    expect *= t->size[i];
+  }
+  return true;
+}
+
+bool fits_int(int64_t v) { return v >= 0 && v <= 0x7fffffffLL; }
+
+int check_desc(const volstn_tensor5 *t) {
+  if (!t) return VOLSTN_ERR_ARG;
+  for (int i = 0; i < 5; i++)
+    if (!fits_int(t->size[i])) return VOLSTN_ERR_ARG;
+  if (t->size[4] > 1 && t->stride[4] != 1) return VOLSTN_ERR_LAYOUT;
+  return VOLSTN_OK;
+}
+
+int64_t numel(const volstn_tensor5 *t) { return t->size[0] * t->size[1] * t->size[2] * t->size[3] * t->size[4]; }
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// shape rules of BilinearSamplerVolumetric.lua:26-42,73
+int check_sampler_shapes(int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid, const volstn_tensor5 *outlike) {
+  if (G != 3 && G != 4) return VOLSTN_ERR_ARG;
+  int st;
+  if ((st = check_desc(vol)) || (st = check_desc(grid)) || (st = check_desc(outlike))) return st;
+  if (grid->size[0] != vol->size[0]) return VOLSTN_ERR_SHAPE;  // lua:33
+  if (grid->size[4] != G) return VOLSTN_ERR_SHAPE;             // lua:34
+  for (int i = 0; i < 4; i++)
+    if (outlike->size[i] != grid->size[i]) return VOLSTN_ERR_SHAPE;  // lua:36-41,73
+  if (outlike->size[4] != vol->size[4]) return VOLSTN_ERR_SHAPE;
+  return VOLSTN_OK;
+}
+
+template <typename real>
+void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                 const volstn_tensor5 *outlike) {
+  a.vol = static_cast<const real *>(vol->data);
+  a.grid = static_cast<const real *>(grid->data);
+  a.out = nullptr;
+  a.gvol = nullptr;
+  a.ggrid = nullptr;
+  a.gout = nullptr;
+  a.B = (int)vol->size[0];
+  a.iD = (int)vol->size[1];
+  a.iH = (int)vol->size[2];
+  a.iW = (int)vol->size[3];
+  a.C = (int)vol->size[4];
+  a.oD = (int)grid->size[1];
+  a.oH = (int)grid->size[2];
+  a.oW = (int)grid->size[3];
+  a.n = (long long)a.oD * a.oH * a.oW;
+  for (int i = 0; i < 4; i++) {
+    a.vs[i] = vol->stride[i];
+    a.gs[i] = grid->stride[i];
+    a.os[i] = outlike->stride[i];
+    a.gvs[i] = 0;
+    a.ggs[i] = 0;
+  }
+  a.dm1 = (real)(a.iD - 1);
+  a.hm1 = (real)(a.iH - 1);
+  a.wm1 = (real)(a.iW - 1);
+}
+
+unsigned generic_blocks(long long total) {
+  long long blocks = (total + kThreads - 1) / kThreads;
+  const long long cap = (long long)kSMs * 64;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)blocks;
+}
+
+int pick_vpt(unsigned flags, int C, long long n) {
+  int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
+  if (vpt == 1 || vpt == 2 || vpt == 4) return vpt;
+  (void)n;
+  return (C <= 2) ? 2 : 1;
+}
+
+// ---- forward launchers ----
+template <int CT, int G>
+int launch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
+  dim3 block(kThreads);
+  auto blocks_x = [&](int v) { return (unsigned)((a.n + (long long)kThreads * v - 1) / ((long long)kThreads * v)); };
+  const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  switch (vpt) {
+    case 4: k_sampler_fwd_packed<float, CT, G, 4><<<dim3(blocks_x(4), by), block, 0, st>>>(a); break;
+    case 2: k_sampler_fwd_packed<float, CT, G, 2><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
+    default: k_sampler_fwd_packed<float, CT, G, 1><<<dim3(blocks_x(1), by), block, 0, st>>>(a); break;
+  }
+  return after_launch();
+}
+
+template <int G>
+int dispatch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
+  switch (a.C) {
+    case 1: return launch_fwd_packed<1, G>(a, vpt, st);
+    case 2: return launch_fwd_packed<2, G>(a, vpt, st);
+    case 3: return launch_fwd_packed<3, G>(a, vpt, st);
+    case 4: return launch_fwd_packed<4, G>(a, vpt, st);
+    default: return launch_fwd_packed<0, G>(a, vpt > 2 ? 2 : vpt, st);
+  }
+}
+
+template <typename real>
+int launch_fwd_generic(const SamplerArgs<real> &a, int G, cudaStream_t st) {
+  const unsigned blocks = generic_blocks(a.n * a.B);
+  if (G == 4)
+    k_sampler_fwd_generic<real, 4><<<blocks, kThreads, 0, st>>>(a);
+  else
+    k_sampler_fwd_generic<real, 3><<<blocks, kThreads, 0, st>>>(a);
+  return after_launch();
+}
+
+// ---- backward launchers ----
+template <int CT, int G, bool OG, bool OV>
+int launch_bwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
+  dim3 block(kThreads);
+  auto blocks_x = [&](int v) { return (unsigned)((a.n + (long long)kThreads * v - 1) / ((long long)kThreads * v)); };
+  const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  switch (vpt) {
+    case 2: k_sampler_bwd_packed<float, CT, G, 2, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
+    default: k_sampler_bwd_packed<float, CT, G, 1, OG, OV><<<dim3(blocks_x(1), by), block, 0, st>>>(a); break;
+  }
+  return after_launch();
+}
+
+template <int G, bool OG, bool OV>
+int dispatch_bwd_packed_c(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
+  switch (a.C) {
+    case 1: return launch_bwd_packed<1, G, OG, OV>(a, vpt, st);
+    case 2: return launch_bwd_packed<2, G, OG, OV>(a, vpt, st);
+    case 3: return launch_bwd_packed<3, G, OG, OV>(a, vpt, st);
+    case 4: return launch_bwd_packed<4, G, OG, OV>(a, vpt, st);
+    default: return launch_bwd_packed<0, G, OG, OV>(a, 1, st);
+  }
+}
+
+template <int G>
+int dispatch_bwd_packed(const SamplerArgs<float> &a, bool og, bool ov, int vpt, cudaStream_t st) {
+  if (og) return dispatch_bwd_packed_c<G, true, false>(a, vpt, st);
+  if (ov) return dispatch_bwd_packed_c<G, false, true>(a, vpt, st);
+  return dispatch_bwd_packed_c<G, false, false>(a, vpt, st);
+}
+
+template <typename real, int G>
+int launch_bwd_generic_g(const SamplerArgs<real> &a, bool og, bool ov, cudaStream_t st) {
+  const unsigned blocks = generic_blocks(a.n * a.B);
+  if (og)
+    k_sampler_bwd_generic<real, G, true, false><<<blocks, kThreads, 0, st>>>(a);
+  else if (ov)
+    k_sampler_bwd_generic<real, G, false, true><<<blocks, kThreads, 0, st>>>(a);
+  else
+    k_sampler_bwd_generic<real, G, false, false><<<blocks, kThreads, 0, st>>>(a);
+  return after_launch();
+}
+
+template <typename real>
+int launch_bwd_generic(const SamplerArgs<real> &a, int G, bool og, bool ov, cudaStream_t st) {
+  return G == 4 ? launch_bwd_generic_g<real, 4>(a, og, ov, st) : launch_bwd_generic_g<real, 3>(a, og, ov, st);
+}
+
+// can the float fast path be used for this set of tensors?
+bool packed_ok(int G, const volstn_tensor5 *vol, std::initializer_list<const volstn_tensor5 *> others) {
+  if (!is_contiguous(vol)) return false;
+  const int64_t C = vol->size[4];
+  const int64_t per_sample = vol->size[1] * vol->size[2] * vol->size[3] * C;
+  if (per_sample >= 0x7fffffffLL) return false;
+  const size_t cal = (C == 4) ? 16 : (C == 2) ? 8 : 4;
+  if (!aligned(vol->data, cal)) return false;
+  for (const volstn_tensor5 *t : others) {
+    if (!t) continue;
+    if (!is_contiguous(t)) return false;
+    const int64_t last = t->size[4];
+    const size_t al = (last == 4) ? 16 : (last == 2) ? 8 : 4;
+    if (!aligned(t->data, al)) return false;
+  }
+  (void)G;
+  return true;
+}
+
+}  // namespace
+
+int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                         const volstn_tensor5 *out, unsigned flags, cudaStream_t st) {
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  int rc = check_sampler_shapes(G, vol, grid, out);
+  if (rc) return rc;
+  if (numel(out) == 0) return VOLSTN_OK;  // nothing to write
+  if (vol->size[1] < 1 || vol->size[2] < 1 || vol->size[3] < 1) return VOLSTN_ERR_SHAPE;
+  if (!vol->data || !grid->data || !out->data) return VOLSTN_ERR_ARG;
+  if (dtype == VOLSTN_F32) {
+    SamplerArgs<float> a;
+    fill_common(a, vol, grid, out);
+    a.out = static_cast<float *>(out->data);
+    if (packed_ok(G, vol, {grid, out})) {
+      const int vpt = pick_vpt(flags, a.C, a.n);
+      return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
+    }
+    return launch_fwd_generic<float>(a, G, st);
+  }
+  SamplerArgs<double> a;
+  fill_common(a, vol, grid, out);
+  a.out = static_cast<double *>(out->data);
+  return launch_fwd_generic<double>(a, G, st);
+}
+
+int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                          const volstn_tensor5 *gradVol, const volstn_tensor5 *gradGrid,
+                          const volstn_tensor5 *gradOut, unsigned flags, cudaStream_t st) {
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID, ov = flags & VOLSTN_BWD_ONLY_VOLUME;
+  if (og && ov) return VOLSTN_ERR_ARG;
+  int rc = check_sampler_shapes(G, vol, grid, gradOut);
+  if (rc) return rc;
+  if (!og) {
+    if ((rc = check_desc(gradVol))) return rc;
+    for (int i = 0; i < 5; i++)
+      if (gradVol->size[i] != vol->size[i]) return VOLSTN_ERR_SHAPE;  // lua:103 resizeAs
+    if (numel(gradVol) && !gradVol->data) return VOLSTN_ERR_ARG;
+  }
+  if (!ov) {
+    if ((rc = check_desc(gradGrid))) return rc;
+    for (int i = 0; i < 5; i++)
+      if (gradGrid->size[i] != grid->size[i]) return VOLSTN_ERR_SHAPE;
+    if (numel(gradGrid) && !gradGrid->data) return VOLSTN_ERR_ARG;
+  }
+  const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
+  if (!og && (flags & VOLSTN_BWD_ZERO_GRADVOL) && numel(gradVol)) {
+    if (!is_contiguous(gradVol)) return VOLSTN_ERR_LAYOUT;
+    VOLSTN_CUDA_TRY(cudaMemsetAsync(gradVol->data, 0, (size_t)numel(gradVol) * esz, st));
+  }
+  if (numel(gradOut) == 0) return VOLSTN_OK;
+  if (vol->size[1] < 1 || vol->size[2] < 1 || vol->size[3] < 1) return VOLSTN_ERR_SHAPE;
+  if (!vol->data || !grid->data || !gradOut->data) return VOLSTN_ERR_ARG;
+
+  if (dtype == VOLSTN_F32) {
+    SamplerArgs<float> a;
+    fill_common(a, vol, grid, gradOut);
+    a.gout = static_cast<const float *>(gradOut->data);
+    if (!og) {
+      a.gvol = static_cast<float *>(gradVol->data);
+      for (int i = 0; i < 4; i++) a.gvs[i] = gradVol->stride[i];
+    }
+    if (!ov) {
+      a.ggrid = static_cast<float *>(gradGrid->data);
+      for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
+    }
+    if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
+      int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
+      if (vpt != 1 && vpt != 2) vpt = 1;
+      return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st) : dispatch_bwd_packed<3>(a, og, ov, vpt, st);
+    }
+    return launch_bwd_generic<float>(a, G, og, ov, st);
+  }
+  SamplerArgs<double> a;
+  fill_common(a, vol, grid, gradOut);
+  a.gout = static_cast<const double *>(gradOut->data);
+  if (!og) {
+    a.gvol = static_cast<double *>(gradVol->data);
+    for (int i = 0; i < 4; i++) a.gvs[i] = gradVol->stride[i];
+  }
+  if (!ov) {
+    a.ggrid = static_cast<double *>(gradGrid->data);
+    for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
+  }
+  return launch_bwd_generic<double>(a, G, og, ov, st);
+}
+
+int sampler_indices_impl(int dtype, int G, const int64_t vol_size[5], const volstn_tensor5 *grid, int32_t *idx,
+                         uint8_t *mask, cudaStream_t st) {
+  if (dtype != VOLSTN_F32 && dtype != VOLSTN_F64) return VOLSTN_ERR_ARG;
+  if (G != 3 && G != 4) return VOLSTN_ERR_ARG;
+  if (!vol_size || !idx || !mask) return VOLSTN_ERR_ARG;
+  int rc = check_desc(grid);
+  if (rc) return rc;
+  if (grid->size[4] != G) return VOLSTN_ERR_SHAPE;
+  volstn_tensor5 vol;
+  vol.data = nullptr;
+  for (int i = 0; i < 5; i++) {
+    if (!fits_int(vol_size[i])) return VOLSTN_ERR_ARG;
+    vol.size[i] = vol_size[i];
+    vol.stride[i] = 0;
+  }
+  if (numel(grid) == 0) return VOLSTN_OK;
+  if (dtype == VOLSTN_F32) {
+    SamplerArgs<float> a;
+    fill_common(a, &vol, grid, grid);
+    a.B = (int)grid->size[0];
+    k_sampler_indices<float><<<generic_blocks(a.n * a.B), kThreads, 0, st>>>(a, idx, mask);
+  } else {
+    SamplerArgs<double> a;
+    fill_common(a, &vol, grid, grid);
+    a.B = (int)grid->size[0];
+    k_sampler_indices<double><<<generic_blocks(a.n * a.B), kThreads, 0, st>>>(a, idx, mask);
+  }
+  return after_launch();
+}
+
+}  // namespace volstn
+
+// =============================================================================================
+// C ABI (DEVICE pointers)
+// =============================================================================================
+extern "C" {
+
+int volstn_b200_sampler_forward(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                                const volstn_tensor5 *out, unsigned flags, void *cuda_stream) {
+  return volstn::sampler_forward_impl(dtype, G, vol, grid, out, flags, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int volstn_b200_sampler_backward(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                                 const volstn_tensor5 *gradVol, const volstn_tensor5 *gradGrid,
+                                 const volstn_tensor5 *gradOut, unsigned flags, void *cuda_stream) {
+  return volstn::sampler_backward_impl(dtype, G, vol, grid, gradVol, gradGrid, gradOut, flags,
+                                       static_cast<cudaStream_t>(cuda_stream));
+}
+
+int volstn_b200_sampler_indices(int dtype, int G, const int64_t vol_size[5], const volstn_tensor5 *grid,
+                                int32_t *idx, uint8_t *mask, void *cuda_stream) {
+  return volstn::sampler_indices_impl(dtype, G, vol_size, grid, idx, mask, static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's Lua ``nn`` modules for the volumetric warp path.
+
+Same class names, constructor arguments, ``updateOutput`` / ``updateGradInput`` protocol, tensor
+layouts ([-1, 1] coordinates, channels-last ``B x D x H x W x C`` volumes, ``B x D x H x W x 4``
+``(z, y, x, .)`` grids), assertions and field names as
+
+* ``nn.BilinearSamplerVolumetric``  -- stn3dtorch/BilinearSamplerVolumetric.lua
+* ``nn.VolumetricGridGenerator``    -- stn3dtorch/VolumetricGridGenerator.lua
+* ``nn.Cumsum``                     -- Cumsum.lua
+
+The Lua files dispatch on the tensor type into a native library
+(``inputImages.nn.BilinearSamplerVolumetric_updateOutput(self, ...)``, lua:74); these classes
+dispatch the same way into the C ABI of include/volstn_b200.h:
+
+* ``torch.cuda.FloatTensor`` / ``DoubleTensor`` -> ``volstn_b200_*``      (device pointers, caller's stream)
+* ``torch.FloatTensor`` / ``DoubleTensor`` (host) -> ``volstn_b200_host_*`` (staged through the GPU)
+
+PyTorch is used for memory and streams only.  There is no CPU or eager fallback: without the
+built library, or without a B200, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _abi
+from ._abi import Tensor5
+
+__all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum"]
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _abi.F32
+    if t.dtype == torch.float64:
+        return _abi.F64
+    raise TypeError(f"volstn: unsupported tensor type {t.dtype} (reference registers Float and Double only, init.c:8-19)")
+
+
+def _desc(t: torch.Tensor) -> Tensor5:
+    assert t.dim() == 5
+    d = Tensor5()
+    d.data = t.data_ptr()
+    for i in range(5):
+        d.size[i] = t.size(i)
+        d.stride[i] = t.stride(i)
+    return d
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+_tls = threading.local()
+_checked_devices = set()
+
+
+def _require_device(index: int) -> None:
+    if index in _checked_devices:
+        return
+    _abi.check(_abi.lib().volstn_b200_device_check(index), f"device {index}")
+    _checked_devices.add(index)
+
+
+def _host_ctx(device: Optional[int] = None) -> ctypes.c_void_p:
+    """One staging context per (thread, device) for host tensors."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if device not in cache:
+        ctx = ctypes.c_void_p()
+        _abi.check(_abi.lib().volstn_b200_host_ctx_create(device, ctypes.byref(ctx)), "host_ctx_create")
+        cache[device] = ctx
+    return cache[device]
+
+
+def _same_place(*ts: torch.Tensor) -> None:
+    dev, dt = ts[0].device, ts[0].dtype
+    for t in ts[1:]:
+        if t.device != dev or t.dtype != dt:
+            raise TypeError("volstn: all tensors of a call must share device and dtype")
+
+
+class Module:
+    """The slice of torch7's nn.Module protocol the warp path uses."""
+
+    def __init__(self):
+        self.output = torch.empty(0)
+        self.gradInput = torch.empty(0)
+
+    def forward(self, input):
+        return self.updateOutput(input)
+
+    def backward(self, input, gradOutput, scale=1):
+        self.updateGradInput(input, gradOutput)
+        return self.gradInput
+
+    def __call__(self, input):
+        return self.forward(input)
+
+    def clearState(self):
+        self.output = torch.empty(0)
+        self.gradInput = torch.empty(0) if not isinstance(self.gradInput, list) else []
+        return self
+
+
+def _add_outer_dim(t: torch.Tensor) -> torch.Tensor:
+    return t.view((1,) + tuple(t.shape))  # addOuterDim, lua:44-52
+
+
+# ------------------------------------------------------------------------------------------------
+# nn.BilinearSamplerVolumetric
+# ------------------------------------------------------------------------------------------------
+class BilinearSamplerVolumetric(Module):
+    """``BilinearSamplerVolumetric:updateOutput({inputImages, grids})`` /
+    ``:updateGradInput({inputImages, grids}, gradOutput)`` (stn3dtorch/BilinearSamplerVolumetric.lua).
+
+    Extras that do not exist in the Lua class (all default to the reference behaviour):
+      gridWidth   4 (the Lua class, lua:34) or 3 (the registered-but-unwrapped BHWD twins, ...c:831-836)
+      onlyGrid    skip gradInput[1]  -- the reference's disabled onlyGrid switch (...c:594, ...cu:1079)
+      onlyVolume  skip gradInput[2]
+      algo / vpt  kernel variant selection for benchmarking (see include/volstn_b200.h)
+    """
+
+    def __init__(self, gridWidth: int = 4, onlyGrid: bool = False, onlyVolume: bool = False, algo: int = 0, vpt: int = 0):
+        super().__init__()
+        self.gradInput = []  # lua:23  self.gradInput = {}
+        assert gridWidth in (3, 4)
+        self.gridWidth = gridWidth
+        self.onlyGrid = onlyGrid
+        self.onlyVolume = onlyVolume
+        self.algo = algo
+        self.vpt = vpt
+
+    # lua:26-42
+    def check(self, input, gradOutput=None):
+        inputImages, grids = input[0], input[1]
+        assert inputImages.is_contiguous(), "Input images have to be contiguous"
+        assert inputImages.dim() == 5
+        assert grids.dim() == 5
+        assert inputImages.size(0) == grids.size(0)  # batch
+        assert grids.size(4) == self.gridWidth  # coordinates
+        if gradOutput is not None:
+            assert grids.size(0) == gradOutput.size(0)
+            assert grids.size(1) == gradOutput.size(1)
+            assert grids.size(2) == gradOutput.size(2)
+            assert grids.size(3) == gradOutput.size(3)
+
+    def _flags(self) -> int:
+        return (self.algo & 0xF00) | _abi.VPT(self.vpt)
+
+    # lua:54-81
+    def updateOutput(self, input):
+        _inputImages, _grids = input[0], input[1]
+        if _inputImages.dim() == 4:
+            inputImages, grids = _add_outer_dim(_inputImages), _add_outer_dim(_grids)
+        else:
+            inputImages, grids = _inputImages, _grids
+        self.check([inputImages, grids])
+        _same_place(inputImages, grids)
+        shape = (inputImages.size(0), grids.size(1), grids.size(2), grids.size(3), inputImages.size(4))
+        out = self.output
+        if (not isinstance(out, torch.Tensor) or tuple(out.shape) != shape or out.dtype != inputImages.dtype
+                or out.device != inputImages.device or not out.is_contiguous()):
+            out = torch.empty(shape, dtype=inputImages.dtype, device=inputImages.device,
+                              pin_memory=(inputImages.device.type == "cpu" and inputImages.is_pinned()))
+        lib = _abi.lib()
+        dt = _dtype_code(inputImages)
+        dv, dg, do = _desc(inputImages), _desc(grids), _desc(out)
+        if inputImages.is_cuda:
+            _require_device(inputImages.device.index)
+            with torch.cuda.device(inputImages.device):
+                rc = lib.volstn_b200_sampler_forward(dt, self.gridWidth, dv, dg, do, self._flags(), _stream(inputImages))
+        else:
+            g = grids if grids.is_contiguous() else grids.contiguous()
+            dg = _desc(g)
+            rc = lib.volstn_b200_host_sampler_forward(_host_ctx(), dt, self.gridWidth, dv, dg, do, self._flags())
+        _abi.check(rc, "BilinearSamplerVolumetric_updateOutput")
+        self.output = out[0] if _inputImages.dim() == 4 else out
+        return self.output
+
+    # lua:83-117
+    def updateGradInput(self, _input, _gradOutput):
+        _inputImages, _grids = _input[0], _input[1]
+        if _inputImages.dim() == 4:
+            inputImages, grids, gradOutput = (_add_outer_dim(_inputImages), _add_outer_dim(_grids),
+                                              _add_outer_dim(_gradOutput))
+        else:
+            inputImages, grids, gradOutput = _inputImages, _grids, _gradOutput
+        self.check([inputImages, grids], gradOutput)
+        _same_place(inputImages, grids, gradOutput)
+        assert gradOutput.size(4) == inputImages.size(4)
+        # lua:101-104  gradInput[i]:resizeAs(input[i]):zero().  The zero-fill of gradInput[1] is
+        # delegated to the library (VOLSTN_BWD_ZERO_GRADVOL, one memset node on the same stream);
+        # gradInput[2] needs none because the kernel assigns every element (...c:819-822).
+        pin = inputImages.device.type == "cpu" and inputImages.is_pinned()
+        gi = self.gradInput if isinstance(self.gradInput, list) else []
+        while len(gi) < 2:
+            gi.append(None)
+
+        def like(cur, ref):
+            if (isinstance(cur, torch.Tensor) and cur.dim() == 5 and tuple(cur.shape) == tuple(ref.shape)
+                    and cur.dtype == ref.dtype and cur.device == ref.device and cur.is_contiguous()):
+                return cur
+            return torch.empty(tuple(ref.shape), dtype=ref.dtype, device=ref.device, pin_memory=pin)
+
+        gradInputImages = like(gi[0], inputImages)
+        gradGrids = like(gi[1], grids)
+        flags = self._flags() | _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gradInputImages.zero_()
+        if self.onlyVolume:
+            flags |= _abi.BWD_ONLY_VOLUME
+            gradGrids.zero_()
+        lib = _abi.lib()
+        dt = _dtype_code(inputImages)
+        if inputImages.is_cuda:
+            _require_device(inputImages.device.index)
+            with torch.cuda.device(inputImages.device):
+                rc = lib.volstn_b200_sampler_backward(dt, self.gridWidth, _desc(inputImages), _desc(grids),
+                                                      _desc(gradInputImages), _desc(gradGrids), _desc(gradOutput),
+                                                      flags, _stream(inputImages))
+        else:
+            g = grids if grids.is_contiguous() else grids.contiguous()
+            go = gradOutput if gradOutput.is_contiguous() else gradOutput.contiguous()
+            rc = lib.volstn_b200_host_sampler_backward(_host_ctx(), dt, self.gridWidth, _desc(inputImages), _desc(g),
+                                                       _desc(gradInputImages), _desc(gradGrids), _desc(go), flags)
+        _abi.check(rc, "BilinearSamplerVolumetric_updateGradInput")
+        if _gradOutput.dim() == 4:
+            self.gradInput = [gradInputImages[0], gradGrids[0]]
+        else:
+            self.gradInput = [gradInputImages, gradGrids]
+        return self.gradInput
+
+    def indices(self, inputImages: torch.Tensor, grids: torch.Tensor):
+        """Debug dump (no Lua counterpart): floor indices (z0,y0,x0) int32 [V,3] and corner masks uint8 [V]."""
+        assert inputImages.is_cuda and grids.is_cuda and grids.dim() == 5
+        n = grids.size(0) * grids.size(1) * grids.size(2) * grids.size(3)
+        idx = torch.empty((n, 3), dtype=torch.int32, device=grids.device)
+        mask = torch.empty((n,), dtype=torch.uint8, device=grids.device)
+        vs = (ctypes.c_int64 * 5)(*[int(s) for s in inputImages.shape])
+        _require_device(grids.device.index)
+        with torch.cuda.device(grids.device):
+            rc = _abi.lib().volstn_b200_sampler_indices(_dtype_code(grids), self.gridWidth, vs, _desc(grids),
+                                                        idx.data_ptr(), mask.data_ptr(), _stream(grids))
+        _abi.check(rc, "sampler_indices")
+        return idx, mask
+
+
+# ------------------------------------------------------------------------------------------------
+# nn.VolumetricGridGenerator
+# ------------------------------------------------------------------------------------------------
+class VolumetricGridGenerator(Module):
+    """``nn.VolumetricGridGenerator(depth, height, width)`` (stn3dtorch/VolumetricGridGenerator.lua).
+
+    Field names ``depth / height / width / baseGrid / batchGrid`` are part of the reference's
+    serialised form (lua:9-24).  ``baseGrid`` is produced on demand by the forward kernel with
+    T = I; the B-replicated ``batchGrid`` (lua:50-55) is never materialised (``batchGrid`` is None).
+    """
+
+    def __init__(self, depth: int, height: int, width: int):
+        super().__init__()
+        assert depth > 1
+        assert height > 1
+        assert width > 1
+        self.depth, self.height, self.width = depth, height, width
+        self.batchGrid = None
+        self._baseGrid = None
+
+    @property
+    def baseGrid(self) -> torch.Tensor:
+        if self._baseGrid is None:
+            eye = torch.eye(4, dtype=torch.float32, device="cuda").view(1, 4, 4)
+            self._baseGrid = self.updateOutput(eye)[0].clone()
+        return self._baseGrid
+
+    # lua:37-65
+    def updateOutput(self, _transformMatrix):
+        transformMatrix = _transformMatrix.view(1, 4, 4) if _transformMatrix.dim() == 2 else _transformMatrix
+        assert (transformMatrix.dim() == 3 and transformMatrix.size(1) == 4 and transformMatrix.size(2) == 4), \
+            "please input affine transform matrices (bx4x4)"
+        T = transformMatrix if transformMatrix.is_contiguous() else transformMatrix.contiguous()
+        B = T.size(0)
+        shape = (B, self.depth, self.height, self.width, 4)
+        out = torch.empty(shape, dtype=T.dtype, device=T.device, pin_memory=(T.device.type == "cpu" and T.is_pinned()))
+        lib = _abi.lib()
+        dt = _dtype_code(T)
+        if T.is_cuda:
+            _require_device(T.device.index)
+            with torch.cuda.device(T.device):
+                rc = lib.volstn_b200_gridgen_forward(dt, T.data_ptr(), out.data_ptr(), B, self.depth, self.height,
+                                                     self.width, _stream(T))
+        else:
+            rc = lib.volstn_b200_host_gridgen_forward(_host_ctx(), dt, T.data_ptr(), out.data_ptr(), B, self.depth,
+                                                      self.height, self.width)
+        _abi.check(rc, "VolumetricGridGenerator_updateOutput")
+        self.output = out[0] if _transformMatrix.dim() == 2 else out
+        return self.output
+
+    # lua:67-90
+    def updateGradInput(self, _transformMatrix, _gradGrid):
+        if _transformMatrix.dim() == 2:
+            transformMatrix, gradGrid = _transformMatrix.view(1, 4, 4), _add_outer_dim(_gradGrid)
+        else:
+            transformMatrix, gradGrid = _transformMatrix, _gradGrid
+        B = transformMatrix.size(0)
+        assert tuple(gradGrid.shape) == (B, self.depth, self.height, self.width, 4)
+        _same_place(transformMatrix, gradGrid)
+        gg = gradGrid if gradGrid.is_contiguous() else gradGrid.contiguous()  # :view() in lua:77 needs it too
+        gradT = torch.empty((B, 4, 4), dtype=gg.dtype, device=gg.device)
+        lib = _abi.lib()
+        dt = _dtype_code(gg)
+        if gg.is_cuda:
+            _require_device(gg.device.index)
+            ws_bytes = lib.volstn_b200_gridgen_backward_workspace(B, self.depth, self.height, self.width)
+            ws = torch.empty((max(int(ws_bytes), 8) + 7) // 8, dtype=torch.float64, device=gg.device)
+            with torch.cuda.device(gg.device):
+                rc = lib.volstn_b200_gridgen_backward(dt, gg.data_ptr(), gradT.data_ptr(), B, self.depth, self.height,
+                                                      self.width, ws.data_ptr(), ws.numel() * 8, _stream(gg))
+        else:
+            rc = lib.volstn_b200_host_gridgen_backward(_host_ctx(), dt, gg.data_ptr(), gradT.data_ptr(), B, self.depth,
+                                                       self.height, self.width)
+        _abi.check(rc, "VolumetricGridGenerator_updateGradInput")
+        self.gradInput = gradT[0] if _transformMatrix.dim() == 2 else gradT
+        return self.gradInput
+
+
+# ------------------------------------------------------------------------------------------------
+# nn.Cumsum
+# ------------------------------------------------------------------------------------------------
+class Cumsum(Module):
+    """``nn.Cumsum()`` (Cumsum.lua): channel i of ``B x N x d1 x .. x dN`` is prefix-summed along
+    spatial axis i; backward is the suffix sum.
+
+    Reference quirk kept by default: ``yxz[i]:squeeze()`` (Cumsum.lua:18) also drops a batch
+    dimension of size 1, so the Lua module fails for B = 1 (it scans the wrong axis for i < N and
+    raises for i = N).  ``allowSingletonBatch=True`` computes the documented semantics instead.
+    """
+
+    def __init__(self, allowSingletonBatch: bool = False):
+        super().__init__()
+        self.allowSingletonBatch = allowSingletonBatch
+        self._gradOutput = None
+
+    def _call(self, x: torch.Tensor, reverse: bool) -> torch.Tensor:
+        if x.dim() < 3 or x.size(1) != x.dim() - 2:
+            raise ValueError("nn.Cumsum expects B x N x d1 x ... x dN (Cumsum.lua:3-6)")
+        if x.size(0) == 1 and not self.allowSingletonBatch:
+            raise ValueError("nn.Cumsum: batch of 1 is broken in the reference (squeeze(), Cumsum.lua:18); "
+                             "pass allowSingletonBatch=True for the documented semantics")
+        x = x if x.is_contiguous() else x.contiguous()  # Cumsum.lua:26-30
+        out = torch.empty_like(x)
+        N = x.size(1)
+        dims = (ctypes.c_int64 * N)(*[int(s) for s in x.shape[2:]])
+        lib = _abi.lib()
+        dt = _dtype_code(x)
+        if x.is_cuda:
+            _require_device(x.device.index)
+            fn = lib.volstn_b200_cumsum_backward if reverse else lib.volstn_b200_cumsum_forward
+            with torch.cuda.device(x.device):
+                rc = fn(dt, x.data_ptr(), out.data_ptr(), x.size(0), N, dims, _stream(x))
+        else:
+            fn = lib.volstn_b200_host_cumsum_backward if reverse else lib.volstn_b200_host_cumsum_forward
+            rc = fn(_host_ctx(), dt, x.data_ptr(), out.data_ptr(), x.size(0), N, dims)
+        _abi.check(rc, "Cumsum")
+        return out
+
+    def updateOutput(self, input):
+        self.output = self._call(input, reverse=False)
+        return self.output
+
+    def updateGradInput(self, input, gradOutput):
+        assert tuple(gradOutput.shape) == tuple(input.shape)
+        self.gradInput = self._call(gradOutput, reverse=True)
+        return self.gradInput
+
+    def clearState(self):
+        self._gradOutput = None  # Cumsum.lua:53-56
+        return super().clearState()

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- sampled voxels/s of nn.BilinearSamplerVolumetric forward + backward at 64^3.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--size 64] [--batch 64] [--channels 1] [--grid g2] [--sweep]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = updateOutput + updateGradInput of the module (gradVol zero-fill included, as
+BilinearSamplerVolumetric.lua:101-104 does it) over one batch of synthetic voxel volumes and an
+ALIGNet-like warp field.  The batch shards over ranks with no collective (samples are independent);
+per-GPU work is fixed, so scaling is "weak".
+
+JSON line (rank 0): metric/value = whole-job sampled voxels/s with inputs resident in HBM;
+`e2e` = the same through the HOST-buffer C ABI (pinned host tensors in, host tensors out, copies
+inside the timed region); `roofline` = the dominant kernel (backward) against the measured HBM
+copy bandwidth; `cpu_baseline` = the reference's own C code on this box's host cores.
+`--impl reference` times only that CPU implementation and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sampled voxels/s fwd+bwd @64^3 (BilinearSamplerVolumetric)"
+UNIT = "voxels/s"
+
+
+def fwd_bytes(C, G=4):
+    return 4 * G + 8 * C            # grid + volume + out            
+
+
+def bwd_bytes(C, G=4):
+    return 8 * G + 12 * C           # grid + gradOut + volume + gradGrid + gradVol
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(name):
+    """dram bytes per launch of the named kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(name)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, in-process so that millisecond regions are still sampled)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.ok = False
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU implementation, timed on the host cores
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_rate(N, C, grid_kind, batch, reps, threads, seed=0):
+    """voxels/s of the reference CPU code (oracle/_ref, else the C port) for fwd+bwd on `batch`
+    samples of the workload, batch-sliced over `threads` host threads; best of `reps`."""
+    from alignet_b200 import synth
+    from oracle import oracle
+    impl = "ref" if oracle.have_ref() else "port"
+    rng = np.random.default_rng(seed)
+    vol = synth.volume("v2", batch, N, N, N, C, rng)
+    grid = synth.grid(grid_kind, batch, N, N, N, rng)
+    go = synth.grad_output(batch, N, N, N, C, rng)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return batch * N ** 3 / best, statistics.mean(times), ("reference" if impl == "ref" else "port")
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm; the others exit 0 without work
+    threads = host_threads()
+    N, C = a.size, a.channels
+    batch = min(a.batch, max(threads, 8))  # bounded sample: one 64^3 sample per host thread
+    from alignet_b200 import synth
+    from oracle import oracle
+    impl = "ref" if oracle.have_ref() else "port"
+    rng = np.random.default_rng(0)
+    vol = synth.volume("v2", batch, N, N, N, C, rng)
+    grid = synth.grid(a.grid, batch, N, N, N, rng)
+    go = synth.grad_output(batch, N, N, N, C, rng)
+    for _ in range(a.warmup):
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+    dt = time.perf_counter() - t0
+    value = batch * N ** 3 * a.steps / dt
+    kind = "reference" if impl == "ref" else "port"
+    sample = (f"{batch} of {a.batch} samples of the {N}^3 C={C} {a.grid} workload per step, "
+              f"batch-sliced over {threads} host threads ({'oracle/_ref = reference C compiled unmodified' if impl == 'ref' else 'oracle C port'}, gcc -O2 -ffp-contract=off)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, batch_override=None):
+    N, C = a.size, a.channels
+    B = batch_override if batch_override is not None else a.batch
+    ws = B * N ** 3 * (2 * 16 + 4 * 4 * C) / 2 ** 20
+    return {"workload": f"BilinearSamplerVolumetric updateOutput+updateGradInput, volume {N}^3 x C={C}, grid {N}^3 x 4 "
+                        f"({a.grid}: {GRID_DESC.get(a.grid, a.grid)}), batch {B} per GPU",
+            "size": N, "channels": C, "batch_per_gpu": B, "grid": a.grid,
+            "l2": f"no flush: working set {ws:.0f} MiB per GPU exceeds the 126 MB L2" if ws > 252 else "L2 flushed (256 MiB write) between timed iterations",
+            "parallelism": f"batch-sharded x{a.gpus}, no data-path collective"}
+
+
+GRID_DESC = {"g1": "identity field", "g2": "ALIGNet-like monotone cage field up-sampled from 8^3",
+             "g3": "uniform random U(-1,1)", "g4": "extreme/out-of-bounds mix", "g5": "random rotations"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from alignet_b200 import _abi, synth
+    from alignet_b200 import nn as vnn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- alignet_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world if distributed else 1
+
+    N, C, B = a.size, a.channels, a.batch
+    V = B * N ** 3
+    rng = np.random.default_rng(1000 + rank)
+    vol_h = torch.from_numpy(synth.volume("v2", B, N, N, N, C, rng)).pin_memory()
+    grid_h = torch.from_numpy(synth.grid(a.grid, B, N, N, N, rng)).pin_memory()
+    go_h = torch.from_numpy(synth.grad_output(B, N, N, N, C, rng)).pin_memory()
+    vol, grid, go = vol_h.cuda(), grid_h.cuda(), go_h.cuda()
+    m = vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)
+    ws_mib = B * N ** 3 * (2 * 16 + 4 * 4 * C) / 2 ** 20
+    flush = None if ws_mib > 252 else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        m.updateOutput([vol, grid])
+        m.updateGradInput([vol, grid], go)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    with sampler:
+        # ---- (1) headline: K steps, CUDA events on the launching stream, max over ranks ----
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _abi.launch_count()
+        if flush is None:
+            ev0.record()
+            for _ in range(a.steps):
+                step()
+            ev1.record()
+            barrier()
+            total_ms = ev0.elapsed_time(ev1)
+        else:
+            total_ms = 0.0
+            for _ in range(a.steps):
+                flush.zero_()
+                ev0.record()
+                step()
+                ev1.record()
+                torch.cuda.synchronize()
+                total_ms += ev0.elapsed_time(ev1)
+            barrier()
+        launches = _abi.launch_count() - n0
+        if distributed:
+            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        ms_per_step = total_ms / a.steps
+        value = V * n_gpus / (ms_per_step * 1e-3)
+
+        # ---- (2) per-kernel durations, same stream, events around each launch ----
+        lib = _abi.lib()
+        d = vnn._desc
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        out = torch.empty((B, N, N, N, C), device="cuda")
+        gv, gg = torch.empty_like(vol), torch.empty_like(grid)
+        flags = (a.algo << 8) | _abi.VPT(a.vpt)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
+        for i in range(a.steps):
+            if flush is not None:
+                flush.zero_()
+            evs[i][0].record()
+            _abi.check(lib.volstn_b200_sampler_forward(0, 4, d(vol), d(grid), d(out), flags, st), "fwd")
+            evs[i][1].record()
+            gv.zero_()
+            evs[i][2].record()
+            _abi.check(lib.volstn_b200_sampler_backward(0, 4, d(vol), d(grid), d(gv), d(gg), d(go), flags, st), "bwd")
+            evs[i][3].record()
+        torch.cuda.synchronize()
+        fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+        zero_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+        bwd_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+
+        # ---- (3) end to end through the HOST-buffer ABI: pinned host in, host out ----
+        e2e = None
+        if not a.no_e2e:
+            mh = vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)
+
+            def host_step():
+                o = mh.updateOutput([vol_h, grid_h])
+                g = mh.updateGradInput([vol_h, grid_h], go_h)
+                return float(o.view(-1)[0]) + float(g[1].view(-1)[0])  # results are host tensors already
+
+            e2e_steps = max(3, min(a.steps, 10))
+            for _ in range(2):
+                host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / e2e_steps
+            if distributed:
+                t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            esz = 4
+            h2d = (vol_h.numel() + grid_h.numel()) * esz + (vol_h.numel() + grid_h.numel() + go_h.numel()) * esz
+            d2h = (go_h.numel() + vol_h.numel() + grid_h.numel()) * esz
+            e2e = {"value": V * n_gpus / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "path": "volstn_b200_host_sampler_forward/backward: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors"}
+    clocks = sampler.summary()
+
+    peak, peak_src = measured_peak()
+    bwd_alg = bwd_bytes(C) * V
+    fwd_alg = fwd_bytes(C) * V
+    bwd_gbs = bwd_alg / (bwd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_sampler_bwd_packed (gradVol scatter-add + gradGrid)",
+                "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
+                "traffic": ncu_traffic("bwd"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bwd_alg, "avg_launch_ms": bwd_ms,
+                "forward": {"achieved": fwd_alg / (fwd_ms * 1e-3) / 1e9, "frac": fwd_alg / (fwd_ms * 1e-3) / 1e9 / peak,
+                            "algorithmic_bytes_per_launch": fwd_alg, "avg_launch_ms": fwd_ms, "traffic": ncu_traffic("fwd")},
+                "gradvol_zero_fill_ms": zero_ms,
+                "step": {"achieved": (fwd_alg + bwd_alg) / (ms_per_step * 1e-3) / 1e9,
+                         "frac": (fwd_alg + bwd_alg) / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "note": "48+20C algorithmic B/voxel over the whole step incl. the gradVol zero-fill"}}
+
+    cpu = None
+    if rank == 0 and not a.no_cpu:
+        threads = host_threads()
+        sample_b = min(B, max(threads, 8))
+        rate, mean_s, kind = cpu_reference_rate(N, C, a.grid, sample_b, reps=2, threads=threads)
+        one_rate, _, _ = cpu_reference_rate(N, C, a.grid, min(B, 4), reps=1, threads=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{sample_b} of {B} samples of the same {N}^3 workload, fwd+bwd, batch-sliced over {threads} host threads, best of 2",
+               "single_core_value": one_rate}
+
+    sweep = run_sweep(a, torch, vnn, synth, _abi) if (a.sweep and rank == 0) else None
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        if sweep is not None:
+            line["sweep"] = sweep
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_sweep(a, torch, vnn, synth, _abi):
+    """BASELINE.json config 4: fwd+bwd over sizes x grids, GB/s against the roofline (rank 0, 1 GPU)."""
+    peak, _ = measured_peak()
+    rows = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for N, B, C in ((32, 32, 1), (32, 256, 1), (64, 64, 1), (64, 256, 1), (128, 8, 1), (128, 32, 1), (128, 8, 4)):
+        for gk in ("g1", "g2", "g3", "g4"):
+            rng = np.random.default_rng(N + B)
+            vol = torch.from_numpy(synth.volume("v2", min(B, 8), N, N, N, C, rng)).cuda().repeat(B // min(B, 8), 1, 1, 1, 1)
+            gs = synth.grid(gk, min(B, 8), N, N, N, rng)
+            grid = torch.from_numpy(gs).cuda().repeat(B // min(B, 8), 1, 1, 1, 1)
+            go = torch.randn((B, N, N, N, C), device="cuda")
+            m = vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)
+            for _ in range(3):
+                m.updateOutput([vol, grid]); m.updateGradInput([vol, grid], go)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            f_ms, b_ms = [], []
+            for _ in range(5):
+                flush.zero_()
+                e[0].record(); m.updateOutput([vol, grid]); e[1].record(); m.updateGradInput([vol, grid], go); e[2].record()
+                torch.cuda.synchronize()
+                f_ms.append(e[0].elapsed_time(e[1])); b_ms.append(e[1].elapsed_time(e[2]))
+            V = B * N ** 3
+            f, b = statistics.median(f_ms), statistics.median(b_ms)
+            rows.append({"N": N, "B": B, "C": C, "grid": gk, "fwd_ms": f, "bwd_ms": b,
+                         "voxels_per_s": V / ((f + b) * 1e-3),
+                         "fwd_frac": fwd_bytes(C) * V / (f * 1e-3) / 1e9 / peak,
+                         "bwd_frac": bwd_bytes(C) * V / (b * 1e-3) / 1e9 / peak,
+                         "step_frac": (fwd_bytes(C) + bwd_bytes(C)) * V / ((f + b) * 1e-3) / 1e9 / peak})
+            del vol, grid, go
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--channels", type=int, default=1)
+    ap.add_argument("--grid", default="g2", choices=list(GRID_DESC))
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 direct red, 2 smem-tile (VOLSTN_ALGO_*)")
+    ap.add_argument("--vpt", type=int, default=0)
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

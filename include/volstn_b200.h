@@ -1,0 +1,192 @@
+/*
+ * volstn_b200.h -- C ABI of the B200-native volumetric warping hot path.
+ *
+ * This header is the drop-in boundary: it sits where stn3dtorch/init.c (CPU library `libvolstn`)
+ * and stn3dtorch/init.cu (CUDA library `libcuvolstn`) sit in the reference.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference root; "...c" is
+ * stn3dtorch/generic/BilinearSamplerVolumetric.c, "...cu" is stn3dtorch/BilinearSamplerVolumetric.cu).
+ * INTEGRATION.md shows the luaT glue a maintainer adds on the reference side, and
+ * alignet_b200/nn.py is the Python mirror of the Lua nn modules that the tests drive.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, element strides; no Torch / PyTorch types.
+ *  - tensors are 5-D descriptors  B x D x H x W x {C | G}  exactly like the reference's
+ *    THTensor (size[], stride[], data).  Strides are in ELEMENTS.  The last dimension must have
+ *    unit stride -- the reference assumes it too (`+ t`, `+ 1`, `+ 2`: ...c:492-495, 556).
+ *  - volume layout channels-last `B x D x H x W x C`; grid `B x D x H x W x G`, components
+ *    (z, y, x[, dis]) in [-1, 1]; -1 -> index 0, +1 -> index size-1; zero padding outside.
+ *  - volstn_b200_* take DEVICE pointers and a CUDA stream (pass the caller's current stream, as
+ *    the reference does with THCState_getCurrentStream, ...cu:706); they launch asynchronously,
+ *    never allocate, never synchronise, never retain pointers.
+ *  - volstn_b200_host_* take HOST pointers (the reference's torch.FloatTensor path, init.c:13-21):
+ *    inputs are staged to the GPU, computed there and copied back inside the call, which returns
+ *    after the results are in the host buffers.  There is NO CPU compute path in this library.
+ *  - every function returns a volstn_status (0 = ok); nothing is thrown, nothing printed.  The
+ *    reference's error convention is `printf + THError("aborting")` (...cu:736-740); the glue
+ *    turns a non-zero status into exactly that.
+ *  - re-entrant: no global mutable state other than an atomic launch counter.
+ */
+#ifndef VOLSTN_B200_H
+#define VOLSTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOLSTN_B200_ABI_VERSION 1
+
+typedef enum volstn_status {
+  VOLSTN_OK = 0,
+  VOLSTN_ERR_ARG = 1,         /* NULL pointer, bad G, bad dtype, negative size                     */
+  VOLSTN_ERR_SHAPE = 2,       /* the asserts of BilinearSamplerVolumetric.lua:26-42 do not hold     */
+  VOLSTN_ERR_LAYOUT = 3,      /* last-dimension stride != 1, or volume not contiguous (lua:30)      */
+  VOLSTN_ERR_CUDA = 4,        /* a CUDA call failed; see volstn_b200_last_cuda_error()              */
+  VOLSTN_ERR_UNSUPPORTED = 5, /* e.g. a sample with >= 2^31 elements                                */
+  VOLSTN_ERR_NO_DEVICE = 6,   /* no sm_100 device: the library refuses to run (no fallback)         */
+  VOLSTN_ERR_WORKSPACE = 7    /* workspace too small                                                */
+} volstn_status;
+
+typedef enum volstn_dtype {
+  VOLSTN_F32 = 0, /* torch.FloatTensor / torch.CudaTensor (init.c:8-9; ...cu is float only) */
+  VOLSTN_F64 = 1  /* torch.DoubleTensor (init.c:18-19)                                      */
+} volstn_dtype;
+
+typedef struct volstn_tensor5 {
+  void *data;        /* device pointer (volstn_b200_*) or host pointer (volstn_b200_host_*) */
+  int64_t size[5];   /* B, D, H, W, C (volume-like) or G (grid-like)                        */
+  int64_t stride[5]; /* element strides; stride[4] must be 1                                 */
+} volstn_tensor5;
+
+/* flags for volstn_b200_sampler_backward ---------------------------------------------------- */
+#define VOLSTN_BWD_ONLY_GRID 0x1u     /* skip gradVol: the reference's onlyGrid switch (...c:594, ...cu:230,1079) */
+#define VOLSTN_BWD_ONLY_VOLUME 0x2u   /* skip gradGrid (its grid is a constant, e.g. the cage up-sample)        */
+#define VOLSTN_BWD_ZERO_GRADVOL 0x4u  /* zero-fill gradVol inside the call (replaces the Lua :zero() of
+                                         BilinearSamplerVolumetric.lua:103); without it gradVol is
+                                         ACCUMULATED into, exactly like the reference                       */
+/* algorithm selection (bits 8..11), 0 = automatic.  Results are identical up to the summation
+ * order of gradVol; exposed so that bench.py / profiles can time each variant. */
+#define VOLSTN_ALGO_SHIFT 8
+#define VOLSTN_ALGO_MASK 0xF00u
+#define VOLSTN_ALGO_AUTO 0x000u
+#define VOLSTN_ALGO_DIRECT 0x100u /* one red.global per in-bounds corner (vector red for C = 2, 4)   */
+#define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA */
+/* voxels per thread (bits 12..15), 0 = automatic */
+#define VOLSTN_VPT_SHIFT 12
+#define VOLSTN_VPT_MASK 0xF000u
+
+/* ---------------------------------------------------------------------------------------------
+ * Sampler (nn.BilinearSamplerVolumetric), DEVICE pointers
+ * ------------------------------------------------------------------------------------------- */
+
+/* Trilinear gather.  Replaces
+ *   G = 4: nn_(BilinearSamplerVolumetric_updateOutput)  ...c:442-583 ; cunn_... ...cu:695-742
+ *   G = 3: nn_(BilinearSamplerBHWD_updateOutput)        ...c:9-167   ; cunn_... ...cu:179-228
+ * Lua stack order (self, vol, grid, out): ...c:444-446.  `out` must be B x gD x gH x gW x C
+ * (BilinearSamplerVolumetric.lua:73); every element of it is overwritten.
+ * out and the floor/mask computation are bit-identical to the reference's CPU float (double)
+ * build compiled without FMA contraction. */
+int volstn_b200_sampler_forward(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                                const volstn_tensor5 *out, unsigned flags, void *cuda_stream);
+
+/* gradInput via scatter-add + gradGrid via the 8-corner derivative.  Replaces
+ *   G = 4: nn_(BilinearSamplerVolumetric_updateGradInput) ...c:585-829 ; cunn_... ...cu:1009-1072
+ *   G = 3: nn_(BilinearSamplerBHWD_updateGradInput)       ...c:169-439 ; cunn_... ...cu:511-575
+ * Lua stack order (self, vol, grid, gradVol, gradGrid, gradOut): ...c:587-591.
+ * gradGrid is assigned (4th component 0 for G = 4, ...c:822); gradVol is accumulated into unless
+ * VOLSTN_BWD_ZERO_GRADVOL.  gradGrid is bit-identical to the reference CPU build; gradVol differs
+ * only by floating-point summation order (atomics), <= 1e-4 * max|ref|. */
+int volstn_b200_sampler_backward(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                                 const volstn_tensor5 *gradVol, const volstn_tensor5 *gradGrid,
+                                 const volstn_tensor5 *gradOut, unsigned flags, void *cuda_stream);
+
+/* Debug dump for the bit-exact parity test: idx[v*3 + {0,1,2}] = (z0, y0, x0) as int32 and
+ * mask[v] bit k = corner k in bounds (k: bit0 = +x, bit1 = +y, bit2 = +z; ...c:542-550), for v in
+ * raster order over (b, z, y, x) of the grid.  vol_size = {B, D, H, W, C}. */
+int volstn_b200_sampler_indices(int dtype, int G, const int64_t vol_size[5], const volstn_tensor5 *grid,
+                                int32_t *idx, uint8_t *mask, void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid generator (nn.VolumetricGridGenerator), DEVICE pointers, contiguous tensors
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[b,z,y,x,:] = T[b] (4x4) . (zn, yn, xn, 1),  zn = -1 + z/(D-1)*2 evaluated in double and
+ * rounded to `dtype` like the Lua constructor (VolumetricGridGenerator.lua:12-23).  Replaces
+ * PGG:updateOutput's batchGrid replication + torch.bmm (VolumetricGridGenerator.lua:50-60); no
+ * B-replicated base grid is materialised.  T: B x 4 x 4, out: B x D x H x W x 4. */
+int volstn_b200_gridgen_forward(int dtype, const void *T, void *out, int64_t B, int64_t D, int64_t H,
+                                int64_t W, void *cuda_stream);
+
+/* gradT[b] (4x4) = sum_v gradGrid[b,v,:]^T (x) base[v,:].  Replaces PGG:updateGradInput's
+ * zero() + baddbmm (VolumetricGridGenerator.lua:79-82).  Deterministic (fixed reduction tree).
+ * workspace: device scratch of at least volstn_b200_gridgen_backward_workspace() bytes. */
+int volstn_b200_gridgen_backward(int dtype, const void *gradGrid, void *gradT, int64_t B, int64_t D,
+                                 int64_t H, int64_t W, void *workspace, size_t workspace_bytes,
+                                 void *cuda_stream);
+size_t volstn_b200_gridgen_backward_workspace(int64_t B, int64_t D, int64_t H, int64_t W);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cumsum (nn.Cumsum), DEVICE pointers, contiguous  B x N x d[0] x ... x d[N-1]  tensors
+ * ------------------------------------------------------------------------------------------- */
+
+/* Channel i is prefix-summed along spatial axis i.  Replaces Cumsum:updateOutput's per-channel
+ * split/squeeze/cumsum (Cumsum.lua:12-22) with one launch.  Prefixes accumulate in double and are
+ * rounded to `dtype` (TH's CPU cumsum uses accreal = double). */
+int volstn_b200_cumsum_forward(int dtype, const void *in, void *out, int64_t B, int N, const int64_t *dims,
+                               void *cuda_stream);
+
+/* gradIn = suffix sum of gradOut along the same axes.  Replaces Cumsum:updateGradInput's
+ * flip / cumsum / flip / copy per channel (Cumsum.lua:39-48) with one launch. */
+int volstn_b200_cumsum_backward(int dtype, const void *gradOut, void *gradIn, int64_t B, int N,
+                                const int64_t *dims, void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HOST-buffer entry points: what `require 'libvolstn'` binds for torch.FloatTensor /
+ * torch.DoubleTensor (init.c:13-21).  Pointers in the descriptors are HOST pointers (pinned memory
+ * gives full PCIe bandwidth; pageable memory works).  The batch is cut into slices that are
+ * pipelined H2D -> kernel -> D2H over several streams; the call returns when the outputs are in
+ * host memory.  A context owns the device staging buffers and streams and may be reused across
+ * calls from one thread at a time; create one per thread for concurrent use.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct volstn_host_ctx volstn_host_ctx;
+
+int volstn_b200_host_ctx_create(int device, volstn_host_ctx **ctx);
+int volstn_b200_host_ctx_destroy(volstn_host_ctx *ctx);
+/* pin / unpin a caller-owned host buffer (cudaHostRegister); optional, for bandwidth only */
+int volstn_b200_host_pin(void *ptr, size_t bytes);
+int volstn_b200_host_unpin(void *ptr);
+
+int volstn_b200_host_sampler_forward(volstn_host_ctx *ctx, int dtype, int G, const volstn_tensor5 *vol,
+                                     const volstn_tensor5 *grid, const volstn_tensor5 *out, unsigned flags);
+int volstn_b200_host_sampler_backward(volstn_host_ctx *ctx, int dtype, int G, const volstn_tensor5 *vol,
+                                      const volstn_tensor5 *grid, const volstn_tensor5 *gradVol,
+                                      const volstn_tensor5 *gradGrid, const volstn_tensor5 *gradOut,
+                                      unsigned flags);
+int volstn_b200_host_gridgen_forward(volstn_host_ctx *ctx, int dtype, const void *T, void *out, int64_t B,
+                                     int64_t D, int64_t H, int64_t W);
+int volstn_b200_host_gridgen_backward(volstn_host_ctx *ctx, int dtype, const void *gradGrid, void *gradT,
+                                      int64_t B, int64_t D, int64_t H, int64_t W);
+int volstn_b200_host_cumsum_forward(volstn_host_ctx *ctx, int dtype, const void *in, void *out, int64_t B,
+                                    int N, const int64_t *dims);
+int volstn_b200_host_cumsum_backward(volstn_host_ctx *ctx, int dtype, const void *gradOut, void *gradIn,
+                                     int64_t B, int N, const int64_t *dims);
+
+/* ---------------------------------------------------------------------------------------------
+ * Utilities
+ * ------------------------------------------------------------------------------------------- */
+int volstn_b200_abi_version(void);
+const char *volstn_b200_strerror(int status);
+/* cudaError_t of the most recent failing CUDA call on the calling thread (0 if none) and its text */
+int volstn_b200_last_cuda_error(void);
+const char *volstn_b200_last_cuda_error_string(void);
+/* VOLSTN_OK iff `device` exists and is compute capability 10.x (the only code this library carries) */
+int volstn_b200_device_check(int device);
+/* number of kernels this library has launched in this process (monotonic, atomic) */
+uint64_t volstn_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLSTN_B200_H */

@@ -1,0 +1,252 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY (CPU checker and CPU baseline).
+
+Nothing under alignet_b200/ imports this module.  It is used by tests/, by
+__graft_entry__.smoke() as the checker, and by bench.py's ``cpu_baseline`` / ``--impl reference``
+legs as the thing timed on the host cores.
+
+Three CPU implementations live here:
+
+* ``ref``      -- the reference's own ``stn3dtorch/generic/BilinearSamplerVolumetric.c`` compiled
+                  UNMODIFIED behind ``oracle/ref_shim.c`` into ``oracle/_ref/`` (float and double).
+                  Only buildable where ``/root/reference`` exists; the built ``.so`` travels.
+* ``port``     -- ``oracle/volstn_oracle.c``, our plain-C restatement (float and double).  Pinned
+                  bit-for-bit against ``ref`` (tests/test_oracle_vs_ref.py) and against the committed
+                  golden vectors (tests/test_oracle_golden.py).
+* numpy restatements of ``Cumsum.lua`` and ``stn3dtorch/VolumetricGridGenerator.lua``.  Those two
+  modules are Lua over Torch7 ``TH`` (``tensor:cumsum``, ``torch.bmm``), which is not vendored in
+  /root/reference and has no pinned version (install.sh:5 clones torch/distro at HEAD), so their
+  parity is UNPINNED: defined by the Lua text plus TH semantics as documented below.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libvolstn_oracle.so")
+REF_SO = {np.dtype(np.float32): os.path.join(HERE, "_ref", "libvolstn_ref_f32.so"),
+          np.dtype(np.float64): os.path.join(HERE, "_ref", "libvolstn_ref_f64.so")}
+
+
+class _Tensor5(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("size", ctypes.c_long * 5), ("stride", ctypes.c_long * 5)]
+
+
+def _desc(a: np.ndarray) -> _Tensor5:
+    assert a.ndim == 5, a.shape
+    assert a.strides[4] == a.itemsize or a.shape[4] == 1, "last dimension must have unit stride"
+    t = _Tensor5()
+    t.data = a.ctypes.data
+    for i in range(5):
+        t.size[i] = a.shape[i]
+        t.stride[i] = a.strides[i] // a.itemsize
+    return t
+
+
+def build(verbose: bool = False) -> None:
+    """Compile the C restatement and, when /root/reference is present, the reference itself."""
+    r = subprocess.run(["make", "-C", HERE, "oracle", "ref"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+_lock = threading.Lock()
+_port = None
+_ref = {}
+
+
+def port_lib():
+    global _port
+    with _lock:
+        if _port is None:
+            if not os.path.exists(PORT_SO):
+                build()
+            _port = ctypes.CDLL(PORT_SO)
+    return _port
+
+
+def have_ref() -> bool:
+    return all(os.path.exists(p) for p in REF_SO.values())
+
+
+def ref_lib(dtype):
+    dtype = np.dtype(dtype)
+    with _lock:
+        if dtype not in _ref:
+            if not os.path.exists(REF_SO[dtype]):
+                raise FileNotFoundError(
+                    f"{REF_SO[dtype]} missing: run `make -C oracle ref` where /root/reference exists")
+            lib = ctypes.CDLL(REF_SO[dtype])
+            assert lib.ref_sizeof_real() == dtype.itemsize
+            _ref[dtype] = lib
+    return _ref[dtype]
+
+
+def _suffix(dtype) -> str:
+    return {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}[np.dtype(dtype)]
+
+
+def _check(vol, grid, G):
+    assert vol.ndim == 5 and grid.ndim == 5 and vol.shape[0] == grid.shape[0]
+    assert grid.shape[4] == G and G in (3, 4)
+    assert vol.dtype == grid.dtype and vol.dtype in (np.float32, np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# sampler: forward / backward / index dump  (impl = "port" | "ref")
+# --------------------------------------------------------------------------------------------
+def sampler_forward(vol: np.ndarray, grid: np.ndarray, G: int = 4, impl: str = "port", out=None) -> np.ndarray:
+    """nn_(BilinearSamplerVolumetric_updateOutput) (G=4, ...c:442) / BilinearSamplerBHWD (G=3, ...c:9)."""
+    _check(vol, grid, G)
+    if out is None:
+        out = np.empty(grid.shape[:4] + (vol.shape[4],), vol.dtype)
+    tv, tg, to = _desc(vol), _desc(grid), _desc(out)
+    if impl == "port":
+        fn = getattr(port_lib(), "oracle_sampler_forward_" + _suffix(vol.dtype))
+        rc = fn(ctypes.c_int(G), ctypes.byref(tv), ctypes.byref(tg), ctypes.byref(to))
+        assert rc == 0
+    else:
+        arr = (_Tensor5 * 3)(tv, tg, to)
+        rc = ref_lib(vol.dtype).ref_call(0 if G == 4 else 2, 3, arr)
+        assert rc == 1
+    return out
+
+
+def sampler_backward(vol, grid, grad_out, G: int = 4, impl: str = "port", grad_vol=None, only_grid=False):
+    """nn_(BilinearSamplerVolumetric_updateGradInput) (...c:585) / BHWD twin (...c:169).
+
+    Returns (gradVol, gradGrid).  gradVol is zero-filled first, as the Lua wrapper does
+    (BilinearSamplerVolumetric.lua:101-104), unless an accumulator is passed in.
+    """
+    _check(vol, grid, G)
+    assert grad_out.shape == grid.shape[:4] + (vol.shape[4],)
+    if grad_vol is None:
+        grad_vol = np.zeros_like(vol)
+    grad_grid = np.zeros_like(grid)
+    ts = [_desc(vol), _desc(grid), _desc(grad_vol), _desc(grad_grid), _desc(grad_out)]
+    if impl == "port":
+        fn = getattr(port_lib(), "oracle_sampler_backward_" + _suffix(vol.dtype))
+        rc = fn(ctypes.c_int(G), *[ctypes.byref(t) for t in ts], ctypes.c_int(int(only_grid)))
+        assert rc == 0
+    else:
+        assert not only_grid, "the reference never enables onlyGrid (...c:594)"
+        arr = (_Tensor5 * 5)(*ts)
+        rc = ref_lib(vol.dtype).ref_call(1 if G == 4 else 3, 5, arr)
+        assert rc == 1
+    return grad_vol, grad_grid
+
+
+def sampler_indices(vol_shape, grid: np.ndarray):
+    """(z0,y0,x0) int32 [V,3] and the 8-bit corner mask uint8 [V] -- port only (a debug dump the
+    reference does not have; the port's values are pinned through the bit-exact output parity)."""
+    n = int(np.prod(grid.shape[:4]))
+    idx = np.empty((n, 3), np.int32)
+    mask = np.empty((n,), np.uint8)
+    size = (ctypes.c_long * 5)(*[int(s) for s in vol_shape])
+    tg = _desc(grid)
+    fn = getattr(port_lib(), "oracle_sampler_indices_" + _suffix(grid.dtype))
+    rc = fn(size, ctypes.byref(tg), idx.ctypes.data_as(ctypes.c_void_p), mask.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return idx, mask
+
+
+def sampler_forward_backward_threaded(vol, grid, grad_out, G=4, impl="ref", threads=1):
+    """Batch-sliced fwd+bwd over `threads` host threads (ctypes releases the GIL).  Valid because
+    samples are independent (batch is the outermost loop, ...c:482,641).  Used only as the timed
+    CPU baseline."""
+    B = vol.shape[0]
+    threads = max(1, min(threads, B))
+    out = np.empty(grid.shape[:4] + (vol.shape[4],), vol.dtype)
+    gv = np.zeros_like(vol)
+    gg = np.zeros_like(grid)
+    bounds = np.linspace(0, B, threads + 1).astype(int)
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi <= lo:
+            return
+        sampler_forward(vol[lo:hi], grid[lo:hi], G, impl, out=out[lo:hi])
+        _, g = sampler_backward(vol[lo:hi], grid[lo:hi], grad_out[lo:hi], G, impl, grad_vol=gv[lo:hi])
+        gg[lo:hi] = g
+
+    if threads == 1:
+        work(0)
+    else:
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    return out, gv, gg
+
+
+# --------------------------------------------------------------------------------------------
+# nn.Cumsum  (Cumsum.lua:12-51)  -- parity UNPINNED (TH arithmetic, see module docstring)
+# --------------------------------------------------------------------------------------------
+def cumsum_forward(x: np.ndarray, accumulate=np.float64) -> np.ndarray:
+    """Cumsum.lua:12-22: channel i (0-based) of a B x N x d1..dN tensor is prefix-summed along
+    spatial axis i.  TH's CPU ``cumsum`` accumulates float tensors in ``accreal`` = double and
+    rounds each prefix to float ([memory]; THTensorMath.c cumsum); THC accumulates in float.
+    ``accumulate`` selects which of the two is restated."""
+    assert x.ndim >= 3 and x.shape[1] == x.ndim - 2, "input must be B x N x d1 x ... x dN"
+    out = np.empty_like(x)
+    for i in range(x.shape[1]):
+        out[:, i] = np.cumsum(x[:, i].astype(accumulate), axis=1 + i, dtype=accumulate).astype(x.dtype)
+    return out
+
+
+def cumsum_backward(grad_out: np.ndarray, accumulate=np.float64) -> np.ndarray:
+    """Cumsum.lua:39-48: flip, cumsum, flip along the same axis  ==  suffix sum."""
+    assert grad_out.ndim >= 3 and grad_out.shape[1] == grad_out.ndim - 2
+    gin = np.empty_like(grad_out)
+    for i in range(grad_out.shape[1]):
+        g = np.flip(grad_out[:, i].astype(accumulate), axis=1 + i)
+        gin[:, i] = np.flip(np.cumsum(g, axis=1 + i, dtype=accumulate), axis=1 + i).astype(grad_out.dtype)
+    return gin
+
+
+# --------------------------------------------------------------------------------------------
+# nn.VolumetricGridGenerator (stn3dtorch/VolumetricGridGenerator.lua) -- parity UNPINNED
+# --------------------------------------------------------------------------------------------
+def gridgen_base(D: int, H: int, W: int, dtype=np.float32) -> np.ndarray:
+    """VolumetricGridGenerator.lua:12-23: (-1 + (k-1)/(n-1)*2) evaluated in Lua doubles, stored in
+    the default tensor type; 4th component 1."""
+    def axis(n):
+        k = np.arange(n, dtype=np.float64)
+        return (-1.0 + k / float(n - 1) * 2.0)
+    base = np.empty((D, H, W, 4), np.float64)
+    base[..., 0] = axis(D)[:, None, None]
+    base[..., 1] = axis(H)[None, :, None]
+    base[..., 2] = axis(W)[None, None, :]
+    base[..., 3] = 1.0
+    return base.astype(dtype)
+
+
+def gridgen_forward(T: np.ndarray, D: int, H: int, W: int, accumulate=np.float64) -> np.ndarray:
+    """VolumetricGridGenerator.lua:58-60: out(B,DHW,4) = batchGrid(B,DHW,4) x T^T(B,4,4).
+    BLAS summation order over the K=4 inner dimension is unspecified, hence a tolerance, and
+    ``accumulate`` brackets it (float64 = exact-ish, float32 = sequential k=0..3)."""
+    assert T.ndim == 3 and T.shape[1:] == (4, 4)
+    base = gridgen_base(D, H, W, T.dtype).reshape(-1, 4)
+    if accumulate == np.float32 and T.dtype == np.float32:
+        out = np.zeros((T.shape[0], base.shape[0], 4), np.float32)
+        for k in range(4):
+            out = out + base[None, :, k, None] * T[:, None, :, k]
+    else:
+        out = np.einsum("vk,bik->bvi", base.astype(accumulate), T.astype(accumulate))
+    return out.astype(T.dtype).reshape(T.shape[0], D, H, W, 4)
+
+
+def gridgen_backward(grad_grid: np.ndarray, accumulate=np.float64) -> np.ndarray:
+    """VolumetricGridGenerator.lua:79-82: gradT(B,4,4) = gradGrid^T(B,4,DHW) x batchGrid(B,DHW,4)."""
+    B, D, H, W, four = grad_grid.shape
+    assert four == 4
+    base = gridgen_base(D, H, W, grad_grid.dtype).reshape(-1, 4)
+    gt = np.einsum("bvi,vj->bij", grad_grid.reshape(B, -1, 4).astype(accumulate), base.astype(accumulate))
+    return gt.astype(grad_grid.dtype)

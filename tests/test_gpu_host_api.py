@@ -1,0 +1,62 @@
+"""HOST-buffer entry points (the torch.FloatTensor path of `libvolstn`, init.c:13-21): host tensors
+in, host tensors out, computed on the GPU in pipelined batch slices.  Must equal the oracle exactly
+like the device path does."""
+import numpy as np
+import pytest
+import torch
+
+from alignet_b200 import nn as vnn, synth
+from oracle import oracle
+from tests._util import bits_equal, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("B,N,C", [(1, 9, 2), (7, 16, 1), (40, 32, 4)])
+def test_host_sampler_matches_oracle(pinned, B, N, C):
+    rng = np.random.default_rng(B * 100 + N + C)
+    vol = synth.volume("v1", B, N, N, N, C, rng)
+    grid = synth.grid("g4", B, N, N, N, rng)
+    go = synth.grad_output(B, N, N, N, C, rng)
+    tv, tg, tgo = torch.from_numpy(vol), torch.from_numpy(grid), torch.from_numpy(go)
+    if pinned:
+        tv, tg, tgo = tv.pin_memory(), tg.pin_memory(), tgo.pin_memory()
+    m = vnn.BilinearSamplerVolumetric()
+    out = m.updateOutput([tv, tg])
+    assert not out.is_cuda
+    ref = oracle.sampler_forward(vol, grid)
+    assert bits_equal(out.numpy(), ref)
+    gv, gg = m.updateGradInput([tv, tg], tgo)
+    rgv, rgg = oracle.sampler_backward(vol, grid, go)
+    assert bits_equal(gg.numpy(), rgg)
+    assert max_rel(gv.numpy(), rgv) <= 1e-4
+
+
+def test_host_double_and_g3():
+    rng = np.random.default_rng(5)
+    vol = synth.volume("v1", 3, 6, 7, 8, 2, rng, np.float64)
+    grid = synth.grid("g3", 3, 5, 6, 7, rng, np.float64, G=3)
+    go = synth.grad_output(3, 5, 6, 7, 2, rng, np.float64)
+    m = vnn.BilinearSamplerVolumetric(gridWidth=3)
+    out = m.updateOutput([torch.from_numpy(vol), torch.from_numpy(grid)])
+    assert bits_equal(out.numpy(), oracle.sampler_forward(vol, grid, 3))
+    gv, gg = m.updateGradInput([torch.from_numpy(vol), torch.from_numpy(grid)], torch.from_numpy(go))
+    rgv, rgg = oracle.sampler_backward(vol, grid, go, 3)
+    assert bits_equal(gg.numpy(), rgg) and max_rel(gv.numpy(), rgv) <= 1e-12
+
+
+def test_host_gridgen_and_cumsum():
+    rng = np.random.default_rng(6)
+    T = rng.standard_normal((5, 4, 4)).astype(np.float32)
+    m = vnn.VolumetricGridGenerator(16, 16, 16)
+    out = m.updateOutput(torch.from_numpy(T))
+    assert not out.is_cuda
+    assert np.max(np.abs(out.numpy() - oracle.gridgen_forward(T, 16, 16, 16))) <= 1e-5
+    gg = rng.standard_normal((5, 16, 16, 16, 4)).astype(np.float32)
+    gt = m.updateGradInput(torch.from_numpy(T), torch.from_numpy(gg))
+    assert max_rel(gt.numpy(), oracle.gridgen_backward(gg)) <= 1e-5
+    x = rng.standard_normal((6, 3, 8, 8, 8)).astype(np.float32)
+    c = vnn.Cumsum()
+    assert bits_equal(c.updateOutput(torch.from_numpy(x)).numpy(), oracle.cumsum_forward(x))
+    assert bits_equal(c.updateGradInput(torch.from_numpy(x), torch.from_numpy(x)).numpy(), oracle.cumsum_backward(x))
