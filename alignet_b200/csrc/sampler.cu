@@ -18,150 +18,43 @@ namespace volstn {
 constexpr int kThreads = 256;
 
 // =============================================================================================
-// per-voxel bodies (packed layout: everything contiguous, 32-bit in-sample offsets)
-// =============================================================================================
-template <typename real, int CT, int G>
-__device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
-                                                     const real *__restrict__ vb, int sD, int sH, int sW,
-                                                     real *__restrict__ o) {
-  using E = Ex<real>;
-  real cw[8];
-  s.corner_weights(cw);
-  const int base = s.base32(sD, sH, sW);
-  if constexpr (CT > 0) {
-    real v[8][CT];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-#pragma unroll
-      for (int t = 0; t < CT; t++) v[k][t] = real(0);  // out-of-bounds corners read as 0 (...c:531-564)
-      if (s.in(k)) {
-        const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
-        ld_channels<real, CT>(vb + off, v[k]);
-      }
-    }
-    real acc[CT];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int k = (G == 4) ? order_xyz(j) : order_zxy(j);  // ...c:566-573 / ...c:149-156
-#pragma unroll
-      for (int t = 0; t < CT; t++) {
-        const real term = E::mul(cw[k], v[k][t]);
-        acc[t] = (j == 0) ? term : E::add(acc[t], term);
-      }
-    }
-    st_channels_stream<real, CT>(o, acc);
-  } else {
-    int off[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) off[k] = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
-    for (int t = 0; t < a.C; t++) {
-      real acc = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int k = (G == 4) ? order_xyz(j) : order_zxy(j);
-        const real v = s.in(k) ? __ldg(vb + off[k] + t) : real(0);
-        const real term = E::mul(cw[k], v);
-        acc = (j == 0) ? term : E::add(acc, term);
-      }
-      o[t] = acc;
-    }
-  }
-}
-
-template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL>
-__device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
-                                                      const real *__restrict__ vb, real *__restrict__ gvb, int sD,
-                                                      int sH, int sW, const real *__restrict__ gop,
-                                                      real *__restrict__ ggp) {
-  using E = Ex<real>;
-  real cw[8];
-  if constexpr (!ONLY_GRID) s.corner_weights(cw);
-  const int base = s.base32(sD, sH, sW);
-  real dot[8];
-  if constexpr (CT > 0) {
-    real go[CT];
-    ld_channels_stream<real, CT>(gop, go);
-    real v[8][CT];
-    if constexpr (!ONLY_VOL) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-#pragma unroll
-        for (int t = 0; t < CT; t++) v[k][t] = real(0);
-        if (s.in(k)) {
-          const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
-          ld_channels<real, CT>(vb + off, v[k]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int off = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
-      if constexpr (!ONLY_VOL) {
-        real d = real(0);  // dot += v * go, channel by channel (...c:736)
-#pragma unroll
-        for (int t = 0; t < CT; t++) d = E::add(d, E::mul(v[k][t], go[t]));
-        dot[k] = s.in(k) ? d : real(0);
-      }
-      if constexpr (!ONLY_GRID) {
-        if (s.in(k)) {
-          real r[CT];
-#pragma unroll
-          for (int t = 0; t < CT; t++) r[t] = E::mul(cw[k], go[t]);  // ...c:737
-          red_channels<real, CT>(gvb + off, r);
-        }
-      }
-    }
-  } else {
-    int off[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      off[k] = base + ((k & 1) ? sW : 0) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0);
-      dot[k] = real(0);
-    }
-    for (int t = 0; t < a.C; t++) {
-      const real go = __ldg(gop + t);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (s.in(k)) {
-          if constexpr (!ONLY_VOL) dot[k] = E::add(dot[k], E::mul(__ldg(vb + off[k] + t), go));
-          if constexpr (!ONLY_GRID) red_add(gvb + off[k] + t, E::mul(cw[k], go));
-        }
-      }
-    }
-  }
-  if constexpr (!ONLY_VOL) {
-    real gz, gy, gx;
-    grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
-    st_grad_grid<real, G>(ggp, gz, gy, gx);
-  }
-}
-
-// =============================================================================================
 // packed kernels: grid.x covers the voxels of one sample (VPT per thread, stride kThreads so every
 // access instruction of a warp is contiguous), grid.y walks the batch.
 // =============================================================================================
+// `fast` is a warp vote: every lane's eight corners are in bounds (tail lanes, which do nothing, vote
+// yes).  The two variants compute the same values; the fast one carries no predicates or selects.
 template <typename real, int CT, int G, int VPT>
 __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
   const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
   for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
-    const real *vb = a.vol + (long long)b * a.vs[0];
-    const real *gb = a.grid + (long long)b * a.n * G;
-    real *ob = a.out + (long long)b * a.n * C;
+    const real *vb = opaque(a.vol + (long long)b * a.vs[0]);
+    const real *gb = opaque(a.grid + (long long)b * a.n * G);
+    real *ob = opaque(a.out + (long long)b * a.n * C);
+    // tail lanes re-read the last voxel (no divergent set-up code) and only skip the store
     real zf[VPT], yf[VPT], xf[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
-      const long long j = j0 + v * kThreads;
-      if (j < a.n) ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+      const long long j = min(j0 + v * kThreads, a.n - 1);
+      ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
     }
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
       const long long j = j0 + v * kThreads;
-      if (j < a.n) {
-        VoxelSetup<real> s;
+      const bool valid = j < a.n;
+      VoxelSetup<real> s;
+      if constexpr (CT > 0) {
+        if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
+          s.finish_fast();
+          if (valid) voxel_forward_ct<real, CT, G, true>(s, vb, sD, sH, ob + j * C);
+        } else {
+          s.finish_exact(a);
+          if (valid) voxel_forward_ct<real, CT, G, false>(s, vb, sD, sH, ob + j * C);
+        }
+      } else {
         s.init(zf[v], yf[v], xf[v], a);
-        voxel_forward_packed<real, CT, G>(a, s, vb, sD, sH, sW, ob + j * C);
+        if (valid) voxel_forward_packed<real, CT, G>(a, s, vb, sD, sH, sW, ob + j * C);
       }
     }
   }
@@ -173,25 +66,39 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerAr
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
   const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
   for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
-    const real *vb = a.vol + (long long)b * a.vs[0];
-    real *gvb = a.gvol + (long long)b * a.gvs[0];
-    const real *gb = a.grid + (long long)b * a.n * G;
-    real *ggb = a.ggrid + (long long)b * a.n * G;
-    const real *gob = a.gout + (long long)b * a.n * C;
+    const real *vb = opaque(a.vol + (long long)b * a.vs[0]);
+    real *gvb = opaque(a.gvol + (long long)b * a.gvs[0]);
+    const real *gb = opaque(a.grid + (long long)b * a.n * G);
+    real *ggb = opaque(a.ggrid + (long long)b * a.n * G);
+    const real *gob = opaque(a.gout + (long long)b * a.n * C);
     real zf[VPT], yf[VPT], xf[VPT];
+    real go[VPT][CT ? CT : 1];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
-      const long long j = j0 + v * kThreads;
-      if (j < a.n) ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+      const long long j = min(j0 + v * kThreads, a.n - 1);
+      ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+      if constexpr (CT > 0) ld_channels_stream<real, CT>(gob + j * C, go[v]);
     }
+    const long long gv_delta = gvb - vb;
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
       const long long j = j0 + v * kThreads;
-      if (j < a.n) {
-        VoxelSetup<real> s;
+      const bool valid = j < a.n;
+      VoxelSetup<real> s;
+      if constexpr (CT > 0) {
+        if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
+          s.finish_fast();
+          if (valid)
+            voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, true>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
+        } else {
+          s.finish_exact(a);
+          if (valid)
+            voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, false>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
+        }
+      } else {
         s.init(zf[v], yf[v], xf[v], a);
-        voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + j * C,
-                                                                 ggb + j * G);
+        if (valid)
+          voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + j * C, ggb + j * G);
       }
     }
   }
@@ -313,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_indices(const SamplerArgs<
     idx_out[idx * 3 + 0] = s.z0;
     idx_out[idx * 3 + 1] = s.y0;
     idx_out[idx * 3 + 2] = s.x0;
-    mask_out[idx] = (uint8_t)s.mask;
+    mask_out[idx] = (uint8_t)s.mask();
   }
 }
 
@@ -386,6 +293,7 @@ void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_t
   a.dm1 = (real)(a.iD - 1);
   a.hm1 = (real)(a.iH - 1);
   a.wm1 = (real)(a.iW - 1);
+  a.fast_dims = (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) ? 1 : 0;
 }
 
 unsigned generic_blocks(long long total) {
@@ -519,6 +427,7 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     fill_common(a, vol, grid, out);
     a.out = static_cast<float *>(out->data);
     if (packed_ok(G, vol, {grid, out})) {
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C)) return launch_fwd_tile(a, G, st);
       const int vpt = pick_vpt(flags, a.C, a.n);
       return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
     }
@@ -572,6 +481,8 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
     }
     if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C))
+        return launch_bwd_tile(a, G, og, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
       if (vpt != 1 && vpt != 2) vpt = 1;
       return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st) : dispatch_bwd_packed<3>(a, og, ov, vpt, st);

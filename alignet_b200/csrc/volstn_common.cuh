@@ -75,11 +75,32 @@ template <> struct Ex<double> {
 //   coord = ((g + 1) * (size - 1)) / 2 ;  i0 = floor(coord) ;  w = 1 - (coord - i0)
 // `sm1` is (real)(size - 1); the division by two is exact, so * 0.5 is the same number.
 template <typename real>
-__device__ __forceinline__ void axis_setup(real g, real sm1, int &i0, real &w) {
+__device__ __forceinline__ real axis_coord(real g, real sm1) {
   using E = Ex<real>;
-  real c = E::mul(E::mul(E::add(g, real(1)), sm1), real(0.5));
+  return E::mul(E::mul(E::add(g, real(1)), sm1), real(0.5));
+}
+template <typename real>
+__device__ __forceinline__ void axis_finish(real c, int &i0, real &w) {
+  using E = Ex<real>;
   i0 = E::floor_to_int(c);
   w = E::sub(real(1), E::sub(c, E::from_int(i0)));
+}
+template <typename real>
+__device__ __forceinline__ void axis_setup(real g, real sm1, int &i0, real &w) {
+  axis_finish<real>(axis_coord<real>(g, sm1), i0, w);
+}
+// floor for 0 <= c < 2^23 (float) without conversion instructions: fl_down(c + 2^23) = 2^23 + floor(c)
+// exactly, its low mantissa bits are floor(c), and subtracting 2^23 again is exact.
+template <typename real>
+__device__ __forceinline__ void axis_finish_fast(real c, int &i0, real &w) {
+  using E = Ex<real>;
+  if constexpr (sizeof(real) == 4) {
+    const float r = __fadd_rd(c, 8388608.0f);
+    i0 = __float_as_int(r) - 0x4B000000;
+    w = E::sub(1.0f, E::sub(c, __fsub_rn(r, 8388608.0f)));
+  } else {
+    axis_finish<real>(c, i0, w);
+  }
 }
 
 // `0 <= i && i <= n-1` for i0 and i0+1 without signed-overflow traps: i0 may be INT_MIN
