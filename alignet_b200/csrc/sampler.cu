@@ -11,6 +11,9 @@
 //   - gradGrid is one 128-bit streaming store,
 //   - the eight corner gathers of a warp fall on four short runs of volume rows (L1-resident for
 //     coherent fields), and gradVol reductions are vector `red.global.add` (C = 2, 4).
+#include <cstdlib>
+#include <cstring>
+
 #include "sampler.cuh"
 
 namespace volstn {
@@ -20,9 +23,15 @@ constexpr int kThreads = 256;
 // =============================================================================================
 // packed kernels: grid.x covers the voxels of one sample (VPT per thread, stride kThreads so every
 // access instruction of a warp is contiguous), grid.y walks the batch.
+//
+// The warp vote selects between two bodies that compute the same values: FAST (all eight corners of
+// all 32 lanes in bounds: no predicates, conversion-free floor) and the exact predicated one.
+// Tail lanes re-read the last voxel (no divergent set-up code) and only skip their stores.
+//
+// Measured and rejected on a B200 (gpurun_out/r1_kbench_pf.txt, r1_kbench_persist.txt): an L2 prefetch
+// of the grid one wave of CTAs ahead (no change) and a persistent, register-pipelined loop (64
+// registers, -30 %).
 // =============================================================================================
-// `fast` is a warp vote: every lane's eight corners are in bounds (tail lanes, which do nothing, vote
-// yes).  The two variants compute the same values; the fast one carries no predicates or selects.
 template <typename real, int CT, int G, int VPT>
 __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
@@ -32,7 +41,6 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
     const real *vb = opaque(a.vol + (long long)b * a.vs[0]);
     const real *gb = opaque(a.grid + (long long)b * a.n * G);
     real *ob = opaque(a.out + (long long)b * a.n * C);
-    // tail lanes re-read the last voxel (no divergent set-up code) and only skip the store
     real zf[VPT], yf[VPT], xf[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
@@ -46,7 +54,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
       VoxelSetup<real> s;
       if constexpr (CT > 0) {
         if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
-          s.finish_fast();
+          s.finish_fast(a, sD, sH, sW);
           if (valid) voxel_forward_ct<real, CT, G, true>(s, vb, sD, sH, ob + j * C);
         } else {
           s.finish_exact(a);
@@ -63,6 +71,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
 template <typename real, int CT, int G, int VPT, bool ONLY_GRID, bool ONLY_VOL>
 __global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
+  constexpr int CR = CT ? CT : 1;
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
   const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
   for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
@@ -71,13 +80,12 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerAr
     const real *gb = opaque(a.grid + (long long)b * a.n * G);
     real *ggb = opaque(a.ggrid + (long long)b * a.n * G);
     const real *gob = opaque(a.gout + (long long)b * a.n * C);
-    real zf[VPT], yf[VPT], xf[VPT];
-    real go[VPT][CT ? CT : 1];
+    real zf[VPT], yf[VPT], xf[VPT], go[VPT][CR];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
       const long long j = min(j0 + v * kThreads, a.n - 1);
       ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
-      if constexpr (CT > 0) ld_channels_stream<real, CT>(gob + j * C, go[v]);
+      if constexpr (CT > 0) ld_channels_stream<real, CR>(gob + j * C, go[v]);
     }
     const long long gv_delta = gvb - vb;
 #pragma unroll
@@ -87,13 +95,13 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerAr
       VoxelSetup<real> s;
       if constexpr (CT > 0) {
         if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
-          s.finish_fast();
+          s.finish_fast(a, sD, sH, sW);
           if (valid)
-            voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, true>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
+            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, true>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
         } else {
           s.finish_exact(a);
           if (valid)
-            voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, false>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
+            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, false>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
         }
       } else {
         s.init(zf[v], yf[v], xf[v], a);
@@ -266,6 +274,21 @@ int check_sampler_shapes(int G, const volstn_tensor5 *vol, const volstn_tensor5 
 }
 
 template <typename real>
+void fill_fast(SamplerArgs<real> &a) {
+  a.fbx = a.fby = a.fbz = 0;
+  a.fneg = 0;
+  if constexpr (sizeof(real) == 4) {
+    if (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) {
+      memcpy(&a.fbx, &a.wm1, 4);
+      memcpy(&a.fby, &a.hm1, 4);
+      memcpy(&a.fbz, &a.dm1, 4);
+      const unsigned sW = (unsigned)a.C, sH = (unsigned)a.iW * sW, sD = (unsigned)a.iH * sH;
+      a.fneg = (int)(0u - 0x4B000000u * (sD + sH + sW));
+    }
+  }
+}
+
+template <typename real>
 void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
                  const volstn_tensor5 *outlike) {
   a.vol = static_cast<const real *>(vol->data);
@@ -293,7 +316,7 @@ void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_t
   a.dm1 = (real)(a.iD - 1);
   a.hm1 = (real)(a.iH - 1);
   a.wm1 = (real)(a.iW - 1);
-  a.fast_dims = (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) ? 1 : 0;
+  fill_fast(a);
 }
 
 unsigned generic_blocks(long long total) {
@@ -301,6 +324,10 @@ unsigned generic_blocks(long long total) {
   const long long cap = (long long)kSMs * 64;
   if (blocks > cap) blocks = cap;
   return (unsigned)blocks;
+}
+
+unsigned ctas_per_sample(long long n, int vpt) {
+  return (unsigned)((n + (long long)kThreads * vpt - 1) / ((long long)kThreads * vpt));
 }
 
 int pick_vpt(unsigned flags, int C, long long n) {
@@ -314,8 +341,8 @@ int pick_vpt(unsigned flags, int C, long long n) {
 template <int CT, int G>
 int launch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   dim3 block(kThreads);
-  auto blocks_x = [&](int v) { return (unsigned)((a.n + (long long)kThreads * v - 1) / ((long long)kThreads * v)); };
   const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 4: k_sampler_fwd_packed<float, CT, G, 4><<<dim3(blocks_x(4), by), block, 0, st>>>(a); break;
     case 2: k_sampler_fwd_packed<float, CT, G, 2><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
@@ -349,8 +376,8 @@ int launch_fwd_generic(const SamplerArgs<real> &a, int G, cudaStream_t st) {
 template <int CT, int G, bool OG, bool OV>
 int launch_bwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   dim3 block(kThreads);
-  auto blocks_x = [&](int v) { return (unsigned)((a.n + (long long)kThreads * v - 1) / ((long long)kThreads * v)); };
   const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 2: k_sampler_bwd_packed<float, CT, G, 2, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
     default: k_sampler_bwd_packed<float, CT, G, 1, OG, OV><<<dim3(blocks_x(1), by), block, 0, st>>>(a); break;
@@ -399,6 +426,8 @@ bool packed_ok(int G, const volstn_tensor5 *vol, std::initializer_list<const vol
   const int64_t C = vol->size[4];
   const int64_t per_sample = vol->size[1] * vol->size[2] * vol->size[3] * C;
   if (per_sample >= 0x7fffffffLL) return false;
+  for (const volstn_tensor5 *t : others)
+    if (t && t->size[1] * t->size[2] * t->size[3] >= 0x7fffffffLL) return false;  // 32-bit voxel indices
   const size_t cal = (C == 4) ? 16 : (C == 2) ? 8 : 4;
   if (!aligned(vol->data, cal)) return false;
   for (const volstn_tensor5 *t : others) {
@@ -484,8 +513,9 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C))
         return launch_bwd_tile(a, G, og, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
-      if (vpt != 1 && vpt != 2) vpt = 1;
-      return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st) : dispatch_bwd_packed<3>(a, og, ov, vpt, st);
+      if (vpt != 1 && vpt != 2) vpt = 2;
+      return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st)
+                    : dispatch_bwd_packed<3>(a, og, ov, vpt, st);
     }
     return launch_bwd_generic<float>(a, G, og, ov, st);
   }

@@ -24,7 +24,10 @@ struct SamplerArgs {
   long long os[4];           // out (fwd) / gradOut (bwd)
   long long gvs[4], ggs[4];  // gradVol, gradGrid
   real dm1, hm1, wm1;        // (real)(iD-1), (real)(iH-1), (real)(iW-1)
-  int fast_dims;             // every extent <= 2^22: the float fast path of VoxelSetup is valid
+  // fast path (float, packed): IEEE bits of wm1/hm1/dm1 (0 disables it, e.g. an extent > 2^22) and the
+  // constant that cancels the 2^23 exponent bits in the offset multiply-adds (see finish_fast)
+  unsigned fbx, fby, fbz;
+  int fneg;
 };
 
 // Everything that depends only on the grid element and the volume extents.
@@ -55,17 +58,35 @@ struct VoxelSetup {
   //            needed.  Same i0, same weight bits as the exact path.
   // finish_exact() : everything else.
   real cz, cy, cx;
+  int fbase;  // finish_fast only: element offset of corner 0 inside the sample
   __device__ __forceinline__ bool begin(real zf, real yf, real xf, const SamplerArgs<real> &a) {
     cx = axis_coord<real>(xf, a.wm1);
     cy = axis_coord<real>(yf, a.hm1);
     cz = axis_coord<real>(zf, a.dm1);
-    return a.fast_dims && cx >= real(0) && cx < a.wm1 && cy >= real(0) && cy < a.hm1 && cz >= real(0) && cz < a.dm1;
+    if constexpr (sizeof(real) == 4) {
+      // for c >= +0 the IEEE bit pattern orders like the value, negative numbers and NaNs have larger
+      // unsigned patterns than any finite positive bound: ONE unsigned compare per axis tests
+      // 0 <= c < size-1
+      return (unsigned)__float_as_int(cx) < a.fbx && (unsigned)__float_as_int(cy) < a.fby &&
+             (unsigned)__float_as_int(cz) < a.fbz;
+    } else {
+      return false;
+    }
   }
-  __device__ __forceinline__ void finish_fast() {
-    axis_finish_fast<real>(cx, x0, wx);
-    axis_finish_fast<real>(cy, y0, wy);
-    axis_finish_fast<real>(cz, z0, wz);
-    ix0 = ix1 = iy0 = iy1 = iz0 = iz1 = true;
+  // sD, sH, sW: element strides of the packed sample (sW = channels)
+  __device__ __forceinline__ void finish_fast(const SamplerArgs<real> &a, int sD, int sH, int sW) {
+    if constexpr (sizeof(real) == 4) {
+      const float rx = __fadd_rd(cx, 8388608.0f), ry = __fadd_rd(cy, 8388608.0f), rz = __fadd_rd(cz, 8388608.0f);
+      wx = __fsub_rn(1.0f, __fsub_rn(cx, __fsub_rn(rx, 8388608.0f)));
+      wy = __fsub_rn(1.0f, __fsub_rn(cy, __fsub_rn(ry, 8388608.0f)));
+      wz = __fsub_rn(1.0f, __fsub_rn(cz, __fsub_rn(rz, 8388608.0f)));
+      // bits(r) = 0x4B000000 + i0.  The offset z0*sD + y0*sH + x0*sW is formed from the raw bits in
+      // wrapping 32-bit arithmetic; a.fneg = -0x4B000000*(sD+sH+sW) cancels the exponent bits, so the
+      // three subtractions cost nothing.
+      fbase = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.fneg), wrap_mul(__float_as_int(ry), sH)),
+                       wrap_mul(__float_as_int(rx), sW));
+      ix0 = ix1 = iy0 = iy1 = iz0 = iz1 = true;
+    }
   }
   __device__ __forceinline__ void finish_exact(const SamplerArgs<real> &a) {
     axis_finish<real>(cx, x0, wx);
@@ -251,11 +272,14 @@ __device__ __forceinline__ T *opaque(T *p) {
 template <typename real>
 struct CornerRows {
   const real *p[4];  // rows (y0,z0) (y0+1,z0) (y0,z0+1) (y0+1,z0+1), each pointing at x0
-  __device__ __forceinline__ CornerRows(const real *sample, const VoxelSetup<real> &s, int sD, int sH, int sW) {
-    p[0] = sample + (long long)s.base32(sD, sH, sW);  // one IMAD.WIDE
-    p[1] = p[0] + sH;                                 // 64-bit add of a uniform
-    p[2] = p[0] + sD;
-    p[3] = p[2] + sH;
+  // `base`: element offset of corner 0 inside the sample (garbage for out-of-range indices, never
+  // dereferenced then).  Four 32-bit offsets, four widening multiply-adds.
+  __device__ __forceinline__ CornerRows(const real *sample, int base, int sD, int sH) {
+    const int t1 = wrap_add(base, sH), t2 = wrap_add(base, sD), t3 = wrap_add(t2, sH);
+    p[0] = sample + base;
+    p[1] = sample + t1;
+    p[2] = sample + t2;
+    p[3] = sample + t3;
   }
   template <int CT>
   __device__ __forceinline__ const real *corner(int k) const { return p[k >> 1] + ((k & 1) ? CT : 0); }
@@ -268,7 +292,7 @@ __device__ __forceinline__ void voxel_forward_ct(const VoxelSetup<real> &s, cons
   static_assert(CT > 0, "compile-time channel count");
   real cw[8];
   s.corner_weights(cw);
-  const CornerRows<real> rows(vb, s, sD, sH, CT);
+  const CornerRows<real> rows(vb, FAST ? s.fbase : s.base32(sD, sH, CT), sD, sH);
   real v[8][CT];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -302,7 +326,7 @@ __device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a,
   } else {
     real cw[8];
     s.corner_weights(cw);
-    const CornerRows<real> rows(vb, s, sD, sH, sW);
+    const CornerRows<real> rows(vb, s.base32(sD, sH, sW), sD, sH);
     for (int t = 0; t < a.C; t++) {
       real acc = 0;
 #pragma unroll
@@ -328,7 +352,8 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
   static_assert(CT > 0, "compile-time channel count");
   real cw[8];
   if constexpr (!ONLY_GRID) s.corner_weights(cw);
-  const CornerRows<real> rows(vb, s, sD, sH, CT);
+  const int base = FAST ? s.fbase : s.base32(sD, sH, CT);
+  const CornerRows<real> rows(vb, base, sD, sH);
   real dot[8];
   if constexpr (!ONLY_VOL) {
     real v[8][CT];
@@ -380,7 +405,7 @@ __device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a
   } else {
     real cw[8];
     if constexpr (!ONLY_GRID) s.corner_weights(cw);
-    const CornerRows<real> rows(vb, s, sD, sH, sW);
+    const CornerRows<real> rows(vb, s.base32(sD, sH, sW), sD, sH);
     const long long gv_delta = gvb - vb;
     real dot[8];
 #pragma unroll

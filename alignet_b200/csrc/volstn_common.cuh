@@ -136,6 +136,10 @@ __device__ __forceinline__ float2 ld_stream_f2(const float2 *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
+// L2 prefetch: no register, no scoreboard.  Used to request the lines a CTA one wave AHEAD will stream,
+// so that HBM always has work queued while resident warps wait on their own gathers.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // streaming (evict-first) stores for write-once outputs
 __device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
