@@ -386,6 +386,7 @@ def run_ours(a):
                "single_core_value": one_rate}
 
     sweep = run_sweep(a, torch, vnn, synth, _abi) if (a.sweep and rank == 0) else None
+    aux = run_aux(a, torch, vnn, synth, _abi, peak) if (rank == 0 and n_gpus == 1 and not a.no_aux) else None
 
     # the same step on the other warp-field families (rank 0, inputs resident, context for the headline)
     fields = None
@@ -421,12 +422,92 @@ def run_ours(a):
                                          if graph is not None else "K steps launched from Python")
         if fields is not None:
             line["other_fields"] = fields
+        if aux is not None:
+            line["aux_kernels"] = aux
         if sweep is not None:
             line["sweep"] = sweep
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_aux(a, torch, vnn, synth, _abi, peak):
+    """SURVEY section 8 rows a7 / a8 and BASELINE.json config 2 (rank 0, N=1): the grid generator and Cumsum
+    kernels and the 32^3 warp pipeline, each timed with an L2 flush before every timed launch."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=10, graph=True):
+        """median device time of fn(); fn is captured into a CUDA graph first so that the Python / ctypes
+        launch cost (tens of us, comparable to these kernels) is not inside the events"""
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        run = fn
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            run = g.replay
+            run()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    res = {}
+    N, B = a.size, a.batch
+    V = B * N ** 3
+    gen = vnn.VolumetricGridGenerator(N, N, N)
+    T = torch.eye(4, device="cuda").repeat(B, 1, 1) + 0.01 * torch.randn(B, 4, 4, device="cuda")
+    gg = torch.randn((B, N, N, N, 4), device="cuda")
+    ms = timed(lambda: gen.updateOutput(T))
+    res["gridgen_forward"] = {"ms": ms, "achieved_gbs": 16 * V / (ms * 1e-3) / 1e9, "frac": 16 * V / (ms * 1e-3) / 1e9 / peak,
+                              "algorithmic_bytes": 16 * V, "note": f"write-only 16 B/voxel, {N}^3 x batch {B}, graph replay, L2 flushed"}
+    ms = timed(lambda: gen.updateGradInput(T, gg))
+    res["gridgen_backward"] = {"ms": ms, "achieved_gbs": 16 * V / (ms * 1e-3) / 1e9, "frac": 16 * V / (ms * 1e-3) / 1e9 / peak,
+                               "algorithmic_bytes": 16 * V, "note": "read-only 16 B/voxel, two-stage deterministic reduction"}
+    del gg
+    csz = 8
+    cs = vnn.Cumsum()
+    d = torch.rand((B, 3, csz, csz, csz), device="cuda")
+    res["cumsum_forward_us"] = timed(lambda: cs.updateOutput(d)) * 1e3
+    res["cumsum_backward_us"] = timed(lambda: cs.updateGradInput(d, d)) * 1e3
+    res["cumsum_note"] = f"B x 3 x {csz}^3 = {d.numel() * 4 / 1024:.0f} KiB: launch-latency bound, reported in us of one graph-replayed launch (the reference needs ~15 launches)"
+
+    # BASELINE.json config 2: Cumsum integration + grid generator + cage up-sample + source warp, 32^3, batch 32
+    Np, Bp = 32, 32
+    rng = np.random.default_rng(5)
+    delta = 2.0 / (csz - 1)
+    dd = torch.from_numpy(np.abs(delta * (1 + 0.25 * rng.standard_normal((Bp, 3, csz, csz, csz)))).astype(np.float32)).cuda()
+    src = torch.from_numpy(synth.volume("v2", Bp, Np, Np, Np, 1, rng)).cuda()
+    gop = torch.from_numpy(synth.grad_output(Bp, Np, Np, Np, 1, rng)).cuda()
+    genp = vnn.VolumetricGridGenerator(Np, Np, Np)
+    eye = torch.eye(4, device="cuda").repeat(Bp, 1, 1)
+    csp, up, warp = vnn.Cumsum(), vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
+    cage_vol = torch.ones((Bp, csz, csz, csz, 4), device="cuda")
+    gcage_in = torch.empty((Bp, 3, csz, csz, csz), device="cuda")
+
+    def pipeline():
+        cage = csp.updateOutput(dd)                                   # integrate the cage deltas
+        cage_vol[..., :3] = (cage + (-1.0 - delta)).permute(0, 2, 3, 4, 1)
+        field_i = genp.updateOutput(eye)                              # identity sampling field
+        field = up.updateOutput([cage_vol, field_i])                  # cage up-sample -> B x 32^3 x 4 field
+        warp.updateOutput([src, field])                               # source warp
+        _, ggrid = warp.updateGradInput([src, field], gop)
+        gcage, _ = up.updateGradInput([cage_vol, field_i], ggrid)
+        gcage_in.copy_(gcage[..., :3].permute(0, 4, 1, 2, 3))
+        csp.updateGradInput(dd, gcage_in)
+
+    ms = timed(pipeline)
+    Vp = Bp * Np ** 3
+    res["pipeline_32"] = {"ms": ms, "voxels_per_s": Vp / (ms * 1e-3),
+                          "workload": f"config 2: Cumsum + grid generator + cage up-sample (8^3 x 4 -> {Np}^3) + source warp, forward and backward, "
+                                      f"{Np}^3 x batch {Bp}, CUDA graph replay, L2 flushed before each replay"}
+    return res
 
 
 def run_sweep(a, torch, vnn, synth, _abi):
@@ -477,6 +558,7 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the grid generator / Cumsum / 32^3 pipeline timings")
     ap.add_argument("--no-graph", action="store_true", help="launch the step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-fields", action="store_true", help="skip the extra per-field (g2, g3) device-resident timings")
     a = ap.parse_args()
