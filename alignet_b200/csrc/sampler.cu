@@ -36,77 +36,126 @@ template <typename real, int CT, int G, int VPT>
 __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
-  const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
-  for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
-    const real *vb = opaque(a.vol + (long long)b * a.vs[0]);
-    const real *gb = opaque(a.grid + (long long)b * a.n * G);
-    real *ob = opaque(a.out + (long long)b * a.n * C);
+  const unsigned n = a.n32;
+  const unsigned j0 = blockIdx.x * (kThreads * VPT) + threadIdx.x;
+  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
+    const size_t sb = (size_t)b * n;  // first voxel of the sample in the packed batch
+    const real *vb = opaque(a.vol + (size_t)b * a.vs32);
+    const real *gb = opaque(a.grid + sb * G);
+    real *ob = opaque(a.out + sb * C);
     real zf[VPT], yf[VPT], xf[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
-      const long long j = min(j0 + v * kThreads, a.n - 1);
-      ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+      const unsigned j = min(j0 + v * kThreads, n - 1);
+      ld_grid<real, G>(gb + (size_t)j * G, zf[v], yf[v], xf[v]);
     }
+    if constexpr (CT > 0) {
+      // one vote for all VPT voxels of the thread: inside the fast block the bodies are straight-line
+      // code, so the gathers of the second voxel are in flight while the first one is summed
+      VoxelSetup<real> s[VPT];
+      int tier = 2;
 #pragma unroll
-    for (int v = 0; v < VPT; v++) {
-      const long long j = j0 + v * kThreads;
-      const bool valid = j < a.n;
-      VoxelSetup<real> s;
-      if constexpr (CT > 0) {
-        if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
-          s.finish_fast(a, sD, sH, sW);
-          if (valid) voxel_forward_ct<real, CT, G, true>(s, vb, sD, sH, ob + j * C);
-        } else {
-          s.finish_exact(a);
-          if (valid) voxel_forward_ct<real, CT, G, false>(s, vb, sD, sH, ob + j * C);
+      for (int v = 0; v < VPT; v++) tier = min(tier, s[v].begin(zf[v], yf[v], xf[v], a));
+      if (__all_sync(0xffffffffu, tier == 2)) {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) s[v].template finish_fast<false>(a, sD, sH, sW);
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          voxel_forward_ct<real, CT, G, 1>(s[v], vb, sD, sH, ob + (size_t)j * C, j < n);
+        }
+      } else if (__all_sync(0xffffffffu, tier >= 1)) {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) s[v].template finish_fast<true>(a, sD, sH, sW);
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          voxel_forward_ct<real, CT, G, 2>(s[v], vb, sD, sH, ob + (size_t)j * C, j < n);
         }
       } else {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          s[v].finish_exact(a);
+          voxel_forward_ct<real, CT, G, 0>(s[v], vb, sD, sH, ob + (size_t)j * C, j < n);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPT; v++) {
+        const unsigned j = j0 + v * kThreads;
+        VoxelSetup<real> s;
         s.init(zf[v], yf[v], xf[v], a);
-        if (valid) voxel_forward_packed<real, CT, G>(a, s, vb, sD, sH, sW, ob + j * C);
+        if (j < n) voxel_forward_packed<real, CT, G>(a, s, vb, sD, sH, sW, ob + (size_t)j * C);
       }
     }
   }
 }
 
 template <typename real, int CT, int G, int VPT, bool ONLY_GRID, bool ONLY_VOL>
-__global__ void __launch_bounds__(kThreads) k_sampler_bwd_packed(const SamplerArgs<real> a) {
+__global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 : 1) k_sampler_bwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
   constexpr int CR = CT ? CT : 1;
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
-  const long long j0 = (long long)blockIdx.x * (kThreads * VPT) + threadIdx.x;
-  for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
-    const real *vb = opaque(a.vol + (long long)b * a.vs[0]);
-    real *gvb = opaque(a.gvol + (long long)b * a.gvs[0]);
-    const real *gb = opaque(a.grid + (long long)b * a.n * G);
-    real *ggb = opaque(a.ggrid + (long long)b * a.n * G);
-    const real *gob = opaque(a.gout + (long long)b * a.n * C);
+  const unsigned n = a.n32;
+  const unsigned j0 = blockIdx.x * (kThreads * VPT) + threadIdx.x;
+  // gradVol is packed like the volume: one pointer difference serves every sample
+  const long long gv_delta = a.gvol - a.vol;
+  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
+    const size_t sb = (size_t)b * n;
+    const real *vb = opaque(a.vol + (size_t)b * a.vs32);
+    real *gvb = const_cast<real *>(vb) + gv_delta;
+    const real *gb = opaque(a.grid + sb * G);
+    real *ggb = opaque(a.ggrid + sb * G);
+    const real *gob = opaque(a.gout + sb * C);
     real zf[VPT], yf[VPT], xf[VPT], go[VPT][CR];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
-      const long long j = min(j0 + v * kThreads, a.n - 1);
+      const size_t j = min(j0 + v * kThreads, n - 1);
       ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
       if constexpr (CT > 0) ld_channels_stream<real, CR>(gob + j * C, go[v]);
     }
-    const long long gv_delta = gvb - vb;
+    if constexpr (CT > 0) {
+      VoxelSetup<real> s[VPT];
+      int tier = 2;
 #pragma unroll
-    for (int v = 0; v < VPT; v++) {
-      const long long j = j0 + v * kThreads;
-      const bool valid = j < a.n;
-      VoxelSetup<real> s;
-      if constexpr (CT > 0) {
-        if (__all_sync(0xffffffffu, s.begin(zf[v], yf[v], xf[v], a))) {
-          s.finish_fast(a, sD, sH, sW);
-          if (valid)
-            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, true>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
-        } else {
-          s.finish_exact(a);
-          if (valid)
-            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, false>(a, s, vb, gv_delta, sD, sH, go[v], ggb + j * G);
+      for (int v = 0; v < VPT; v++) tier = min(tier, s[v].begin(zf[v], yf[v], xf[v], a));
+      if (__all_sync(0xffffffffu, tier == 2)) {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) s[v].template finish_fast<false>(a, sD, sH, sW);
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1>(a, s[v], vb, gv_delta, sD, sH, go[v],
+                                                                 ggb + (size_t)j * G, j < n);
+        }
+      } else if (__all_sync(0xffffffffu, tier >= 1)) {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) s[v].template finish_fast<true>(a, sD, sH, sW);
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 2>(a, s[v], vb, gv_delta, sD, sH, go[v],
+                                                                 ggb + (size_t)j * G, j < n);
         }
       } else {
+#pragma unroll
+        for (int v = 0; v < VPT; v++) {
+          const unsigned j = j0 + v * kThreads;
+          s[v].finish_exact(a);
+          voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 0>(a, s[v], vb, gv_delta, sD, sH, go[v],
+                                                                 ggb + (size_t)j * G, j < n);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPT; v++) {
+        const unsigned j = j0 + v * kThreads;
+        VoxelSetup<real> s;
         s.init(zf[v], yf[v], xf[v], a);
-        if (valid)
-          voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + j * C, ggb + j * G);
+        if (j < n)
+          voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + (size_t)j * C,
+                                                                  ggb + (size_t)j * G);
       }
     }
   }
@@ -277,6 +326,7 @@ template <typename real>
 void fill_fast(SamplerArgs<real> &a) {
   a.fbx = a.fby = a.fbz = 0;
   a.fneg = 0;
+  a.border_ok = 0;
   if constexpr (sizeof(real) == 4) {
     if (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) {
       memcpy(&a.fbx, &a.wm1, 4);
@@ -284,6 +334,7 @@ void fill_fast(SamplerArgs<real> &a) {
       memcpy(&a.fbz, &a.dm1, 4);
       const unsigned sW = (unsigned)a.C, sH = (unsigned)a.iW * sW, sD = (unsigned)a.iH * sH;
       a.fneg = (int)(0u - 0x4B000000u * (sD + sH + sW));
+      a.border_ok = 1;
     }
   }
 }
@@ -317,6 +368,8 @@ void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_t
   a.hm1 = (real)(a.iH - 1);
   a.wm1 = (real)(a.iW - 1);
   fill_fast(a);
+  a.n32 = (unsigned)a.n;
+  a.vs32 = (unsigned)vol->stride[0];
 }
 
 unsigned generic_blocks(long long total) {
@@ -455,6 +508,8 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     SamplerArgs<float> a;
     fill_common(a, vol, grid, out);
     a.out = static_cast<float *>(out->data);
+    if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
+    if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     if (packed_ok(G, vol, {grid, out})) {
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C)) return launch_fwd_tile(a, G, st);
       const int vpt = pick_vpt(flags, a.C, a.n);
@@ -509,6 +564,8 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       a.ggrid = static_cast<float *>(gradGrid->data);
       for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
     }
+    if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
+    if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C))
         return launch_bwd_tile(a, G, og, ov, st);

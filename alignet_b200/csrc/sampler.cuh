@@ -28,6 +28,10 @@ struct SamplerArgs {
   // constant that cancels the 2^23 exponent bits in the offset multiply-adds (see finish_fast)
   unsigned fbx, fby, fbz;
   int fneg;
+  // packed kernels: voxels per sample and elements per volume sample as 32-bit numbers (both < 2^31), so
+  // that the per-CTA base pointers are one widening multiply each
+  unsigned n32, vs32;
+  int border_ok;  // 0 disables the border tier (VOLSTN_DEBUG_NO_BORDER, A/B timing only)
 };
 
 // Everything that depends only on the grid element and the volume extents.
@@ -59,21 +63,27 @@ struct VoxelSetup {
   // finish_exact() : everything else.
   real cz, cy, cx;
   int fbase;  // finish_fast only: element offset of corner 0 inside the sample
-  __device__ __forceinline__ bool begin(real zf, real yf, real xf, const SamplerArgs<real> &a) {
+  // tier of this voxel: 2 = every corner in bounds (0 <= c < size-1 on every axis), 1 = inside the volume
+  // including its high faces (0 <= c <= size-1: only high corners with weight exactly 0 can be out of
+  // bounds), 0 = anything else (outside, NaN, huge)
+  __device__ __forceinline__ int begin(real zf, real yf, real xf, const SamplerArgs<real> &a) {
     cx = axis_coord<real>(xf, a.wm1);
     cy = axis_coord<real>(yf, a.hm1);
     cz = axis_coord<real>(zf, a.dm1);
     if constexpr (sizeof(real) == 4) {
       // for c >= +0 the IEEE bit pattern orders like the value, negative numbers and NaNs have larger
       // unsigned patterns than any finite positive bound: ONE unsigned compare per axis tests
-      // 0 <= c < size-1
-      return (unsigned)__float_as_int(cx) < a.fbx && (unsigned)__float_as_int(cy) < a.fby &&
-             (unsigned)__float_as_int(cz) < a.fbz;
+      // 0 <= c < size-1 (or <=)
+      const unsigned ux = (unsigned)__float_as_int(cx), uy = (unsigned)__float_as_int(cy), uz = (unsigned)__float_as_int(cz);
+      const bool strict = ux < a.fbx && uy < a.fby && uz < a.fbz;
+      const bool inside = ux <= a.fbx && uy <= a.fby && uz <= a.fbz && a.border_ok;
+      return strict ? 2 : (inside ? 1 : 0);
     } else {
-      return false;
+      return 0;
     }
   }
   // sD, sH, sW: element strides of the packed sample (sW = channels)
+  template <bool BORDER = false>
   __device__ __forceinline__ void finish_fast(const SamplerArgs<real> &a, int sD, int sH, int sW) {
     if constexpr (sizeof(real) == 4) {
       const float rx = __fadd_rd(cx, 8388608.0f), ry = __fadd_rd(cy, 8388608.0f), rz = __fadd_rd(cz, 8388608.0f);
@@ -85,7 +95,14 @@ struct VoxelSetup {
       // three subtractions cost nothing.
       fbase = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.fneg), wrap_mul(__float_as_int(ry), sH)),
                        wrap_mul(__float_as_int(rx), sW));
-      ix0 = ix1 = iy0 = iy1 = iz0 = iz1 = true;
+      ix0 = iy0 = iz0 = true;
+      if constexpr (BORDER) {  // c == size-1: i0 = size-1, the high corner is out of bounds (its weight is 0)
+        ix1 = (unsigned)__float_as_int(cx) < a.fbx;
+        iy1 = (unsigned)__float_as_int(cy) < a.fby;
+        iz1 = (unsigned)__float_as_int(cz) < a.fbz;
+      } else {
+        ix1 = iy1 = iz1 = true;
+      }
     }
   }
   __device__ __forceinline__ void finish_exact(const SamplerArgs<real> &a) {
@@ -285,14 +302,15 @@ struct CornerRows {
   __device__ __forceinline__ const real *corner(int k) const { return p[k >> 1] + ((k & 1) ? CT : 0); }
 };
 
-template <typename real, int CT, int G, bool FAST>
+template <typename real, int CT, int G, int MODE>
 __device__ __forceinline__ void voxel_forward_ct(const VoxelSetup<real> &s, const real *__restrict__ vb, int sD,
-                                                 int sH, real *__restrict__ o) {
+                                                 int sH, real *__restrict__ o, bool valid = true) {
   using E = Ex<real>;
   static_assert(CT > 0, "compile-time channel count");
   real cw[8];
   s.corner_weights(cw);
-  const CornerRows<real> rows(vb, FAST ? s.fbase : s.base32(sD, sH, CT), sD, sH);
+  constexpr bool FAST = MODE == 1;
+  const CornerRows<real> rows(vb, MODE ? s.fbase : s.base32(sD, sH, CT), sD, sH);
   real v[8][CT];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -313,7 +331,7 @@ __device__ __forceinline__ void voxel_forward_ct(const VoxelSetup<real> &s, cons
       acc[t] = (j == 0) ? term : E::add(acc[t], term);
     }
   }
-  st_channels_stream<real, CT>(o, acc);
+  if (valid) st_channels_stream<real, CT>(o, acc);  // tail lanes compute a clamped voxel and drop it
 }
 
 template <typename real, int CT, int G>
@@ -322,7 +340,7 @@ __device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a,
                                                      real *__restrict__ o) {
   using E = Ex<real>;
   if constexpr (CT > 0) {
-    voxel_forward_ct<real, CT, G, false>(s, vb, sD, sH, o);
+    voxel_forward_ct<real, CT, G, 0>(s, vb, sD, sH, o);
   } else {
     real cw[8];
     s.corner_weights(cw);
@@ -344,15 +362,16 @@ __device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a,
 // go[] = gradOut of this voxel (already loaded).  gv_delta = gradVol sample base - volume sample base
 // in elements (both tensors are packed with identical strides), so corner k of gradVol is
 // rows.corner(k) + gv_delta.
-template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL, bool FAST>
+template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL, int MODE>
 __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
                                                   const real *__restrict__ vb, long long gv_delta, int sD, int sH,
-                                                  const real (&go)[CT], real *__restrict__ ggp) {
+                                                  const real (&go)[CT], real *__restrict__ ggp, bool valid = true) {
   using E = Ex<real>;
   static_assert(CT > 0, "compile-time channel count");
   real cw[8];
   if constexpr (!ONLY_GRID) s.corner_weights(cw);
-  const int base = FAST ? s.fbase : s.base32(sD, sH, CT);
+  constexpr bool FAST = MODE == 1;
+  const int base = MODE ? s.fbase : s.base32(sD, sH, CT);
   const CornerRows<real> rows(vb, base, sD, sH);
   real dot[8];
   if constexpr (!ONLY_VOL) {
@@ -377,7 +396,7 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
   if constexpr (!ONLY_GRID) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      if (FAST || s.in(k)) {
+      if (valid && (FAST || s.in(k))) {
         real r[CT];
 #pragma unroll
         for (int t = 0; t < CT; t++) r[t] = E::mul(cw[k], go[t]);  // ...c:737
@@ -388,7 +407,7 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
   if constexpr (!ONLY_VOL) {
     real gz, gy, gx;
     grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
-    st_grad_grid<real, G>(ggp, gz, gy, gx);
+    if (valid) st_grad_grid<real, G>(ggp, gz, gy, gx);
   }
 }
 
@@ -401,7 +420,7 @@ __device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a
   if constexpr (CT > 0) {
     real go[CT];
     ld_channels_stream<real, CT>(gop, go);
-    voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, false>(a, s, vb, gvb - vb, sD, sH, go, ggp);
+    voxel_backward_ct<real, CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp);
   } else {
     real cw[8];
     if constexpr (!ONLY_GRID) s.corner_weights(cw);

@@ -121,48 +121,45 @@ __device__ __forceinline__ constexpr int order_zxy(int j) { return ((j & 1) << 2
 // L1 is kept for the volume gather.
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
 }
 __device__ __forceinline__ float ld_stream_f1(const float *p) {
   float r;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float2 ld_stream_f2(const float2 *p) {
   float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
 // L2 prefetch: no register, no scoreboard.  Used to request the lines a CTA one wave AHEAD will stream,
 // so that HBM always has work queued while resident warps wait on their own gathers.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// streaming (evict-first) stores for write-once outputs
-__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_stream_f2(float2 *p, float2 v) {
-  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void st_stream_f1(float *p, float v) {
-  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
+// streaming (evict-first) stores for write-once outputs.  Compiler intrinsics, NOT asm with a "memory"
+// clobber: a clobber is a compiler barrier, and the gathers of a thread's second voxel must be free to
+// move above the first voxel's store (these outputs are never read back inside a kernel).
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_f2(float2 *p, float2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_f1(float *p, float v) { __stcs(p, v); }
 
-// fire-and-forget reductions into gradVol (REDG.E.ADD.F32 / .F32x2 / .F32x4 on sm_100a)
+// fire-and-forget reductions into gradVol (REDG.E.ADD.F32 / .F32x2 / .F32x4 on sm_100a).  volatile (they
+// have no outputs) but no "memory" clobber, for the same reason: gradVol is write-only inside a kernel.
 __device__ __forceinline__ void red_add(float *p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));
 }
 __device__ __forceinline__ void red_add2(float *p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b));
 }
 __device__ __forceinline__ void red_add4(float *p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 __device__ __forceinline__ void red_add(double *p, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
 
 }  // namespace volstn
