@@ -18,7 +18,7 @@ F32, F64 = 0, 1
 BWD_ONLY_GRID = 0x1
 BWD_ONLY_VOLUME = 0x2
 BWD_ZERO_GRADVOL = 0x4
-ALGO_AUTO, ALGO_DIRECT, ALGO_TILE = 0x000, 0x100, 0x200
+ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR = 0x000, 0x100, 0x200, 0x300
 VPT_SHIFT = 12
 
 

@@ -23,11 +23,15 @@ LIB = os.path.join(CSRC, "libvolstn_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
-HEADERS = ["volstn_common.cuh", "sampler.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
+HEADERS = ["volstn_common.cuh", "sampler.cuh", "sampler_pair.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
+    # never contract a multiply and an add: parity is defined on the reference's unfused operation order.  The
+    # scalar __f*_rn intrinsics already guarantee it; the packed __fmul2_rn/__fadd2_rn ones do NOT (ptxas
+    # fused them into FFMA2), so contraction is switched off for the whole library.
+    "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",

@@ -32,6 +32,8 @@ struct SamplerArgs {
   // that the per-CTA base pointers are one widening multiply each
   unsigned n32, vs32;
   int border_ok;  // 0 disables the border tier (VOLSTN_DEBUG_NO_BORDER, A/B timing only)
+  float one;      // 1.0f, opaque to the optimiser (sampler_pair.cuh::P2)
+  int no_pair;    // host only: use the scalar VPT = 2 kernels instead of the FADD2/FMUL2 pair kernels
 };
 
 // Everything that depends only on the grid element and the volume extents.
@@ -394,6 +396,11 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
     }
   }
   if constexpr (!ONLY_GRID) {
+    // Measured and rejected on a B200 (gpurun_out/r1_kbench_{nzskip,rowskip,xmerge}.txt): skipping
+    // reductions whose addend is an exact zero (per lane, or per row with a warp vote: 20 M -> 5.8 M L2
+    // reduction sector-ops with the identity field, same run time -- the kernel is then issue-bound) and
+    // merging x-adjacent contributions across lanes with shuffles (the identity grid's coordinates are one
+    // ulp below an integer 36 % of the time, so only ~30 % of the neighbours line up).
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       if (valid && (FAST || s.in(k))) {

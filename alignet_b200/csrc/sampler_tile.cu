@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(BZ * 64, BZ == 8 ? 2 : 4)
     const long long cells = (long long)box.ext[0] * box.ext[1] * pitch;
     if (cells <= 0) {
       // every corner of every voxel is out of bounds: no loads, no reductions; gradGrid = 0 * weights
-      if (valid) voxel_backward_ct<float, CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp);
+      voxel_backward_ct<float, CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp, valid);
     } else if (cells <= cap_cells) {
       if constexpr (!ONLY_GRID) {
         for (int i = threadIdx.x; i < (int)cells * CT; i += NT) s_gv[i] = 0.f;
@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(BZ * 64, BZ == 8 ? 2 : 4)
           if (nz) red_channels<float, CT>(gvb + go_, v);
         });
       }
-    } else if (valid) {
-      voxel_backward_ct<float, CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp);
+    } else {
+      voxel_backward_ct<float, CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp, valid);
     }
     if (b + (int)gridDim.y < a.B) __syncthreads();
   }

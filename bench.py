@@ -203,7 +203,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
 
-    from alignet_b200 import _abi, synth
+    from alignet_b200 import _abi, shard, synth
     from alignet_b200 import nn as vnn
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,6 +214,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
+        # NCCL logs (even its version banner) go to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world if distributed else 1
 
@@ -287,9 +289,7 @@ def run_ours(a):
             barrier()
         launches = (launches_per_step * a.steps) if graph is not None else (_abi.launch_count() - n0)
         if distributed:
-            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
+            total_ms = shard.max_over_ranks(total_ms, device="cuda")
         ms_per_step = total_ms / a.steps
         value = V * n_gpus / (ms_per_step * 1e-3)
 
@@ -349,9 +349,7 @@ def run_ours(a):
             barrier()
             e2e_s = (time.perf_counter() - t0) / e2e_steps
             if distributed:
-                t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                e2e_s = float(t.item())
+                e2e_s = shard.max_over_ranks(e2e_s, device="cuda")
             esz = 4
             h2d = (vol_h.numel() + grid_h.numel()) * esz + (vol_h.numel() + grid_h.numel() + go_h.numel()) * esz
             d2h = (go_h.numel() + vol_h.numel() + grid_h.numel()) * esz

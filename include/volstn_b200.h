@@ -73,6 +73,7 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_ALGO_AUTO 0x000u
 #define VOLSTN_ALGO_DIRECT 0x100u /* one red.global per in-bounds corner (vector red for C = 2, 4)   */
 #define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA */
+#define VOLSTN_ALGO_PAIR 0x300u   /* direct kernels with packed fp32x2 arithmetic (measured slower; kept for A/B) */
 /* debugging / A-B timing: force the slower but always-valid code paths (results are identical) */
 #define VOLSTN_DEBUG_NO_FAST 0x10000u   /* every warp takes the exact predicated path            */
 #define VOLSTN_DEBUG_NO_BORDER 0x20000u /* warps touching a high face take the exact path (no border tier) */
