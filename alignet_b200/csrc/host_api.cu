@@ -19,6 +19,15 @@ struct volstn_host_ctx {
   cudaStream_t stream[kSlots];
   void *arena[kSlots];
   size_t cap[kSlots];
+  // Device copies of the last forward call's inputs (VOLSTN_HOST_KEEP_INPUTS), reused by the next backward
+  // call on the same host tensors (VOLSTN_HOST_REUSE_INPUTS).  nn.Module's contract makes this legal for
+  // the Lua / Python modules: updateGradInput(input, gradOutput) assumes updateOutput(input) ran before on
+  // the same input.  Keyed by host pointer, shape and dtype; invalid after any other host sampler call.
+  void *keep_vol, *keep_grid;
+  size_t keep_vol_cap, keep_grid_cap;
+  bool keep_valid;
+  int keep_dtype;
+  volstn_tensor5 keep_vol_key, keep_grid_key;
 };
 
 namespace volstn {
@@ -78,6 +87,25 @@ volstn_tensor5 slice_desc(const volstn_tensor5 *t, int64_t b0, int64_t nb, void 
   return d;
 }
 
+bool same_desc(const volstn_tensor5 &a, const volstn_tensor5 &b) {
+  if (a.data != b.data) return false;
+  for (int i = 0; i < 5; i++)
+    if (a.size[i] != b.size[i] || a.stride[i] != b.stride[i]) return false;
+  return true;
+}
+
+int ensure_keep(volstn_host_ctx *c, void **buf, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return VOLSTN_OK;
+  int rc = sync_all(c);
+  if (rc) return rc;
+  if (*buf) VOLSTN_CUDA_TRY(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  VOLSTN_CUDA_TRY(cudaMalloc(buf, bytes));
+  *cap = bytes;
+  return VOLSTN_OK;
+}
+
 size_t sample_elems(const volstn_tensor5 *t) { return (size_t)(t->size[1] * t->size[2] * t->size[3] * t->size[4]); }
 
 }  // namespace
@@ -102,6 +130,9 @@ int volstn_b200_host_ctx_create(int device, volstn_host_ctx **out) {
     c->cap[s] = 0;
     c->stream[s] = nullptr;
   }
+  c->keep_vol = c->keep_grid = nullptr;
+  c->keep_vol_cap = c->keep_grid_cap = 0;
+  c->keep_valid = false;
   for (int s = 0; s < volstn_host_ctx::kSlots; s++) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -123,6 +154,8 @@ int volstn_b200_host_ctx_destroy(volstn_host_ctx *c) {
     }
     if (c->arena[s]) cudaFree(c->arena[s]);
   }
+  if (c->keep_vol) cudaFree(c->keep_vol);
+  if (c->keep_grid) cudaFree(c->keep_grid);
   delete c;
   return VOLSTN_OK;
 }
@@ -157,6 +190,12 @@ int volstn_b200_host_sampler_forward(volstn_host_ctx *c, int dtype, int G, const
   const int64_t bs = slice_batch(B, nv + ng + no);
   const size_t need = align_up(nv * bs) + align_up(ng * bs) + align_up(no * bs);
   int rc = VOLSTN_OK;
+  const bool keep = flags & VOLSTN_HOST_KEEP_INPUTS;
+  c->keep_valid = false;
+  if (keep) {
+    if ((rc = ensure_keep(c, &c->keep_vol, &c->keep_vol_cap, nv * B))) return rc;
+    if ((rc = ensure_keep(c, &c->keep_grid, &c->keep_grid_cap, ng * B))) return rc;
+  }
   int slice = 0;
   for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
     const int64_t nb = std::min(bs, B - b0);
@@ -165,6 +204,10 @@ int volstn_b200_host_sampler_forward(volstn_host_ctx *c, int dtype, int G, const
     char *dv = static_cast<char *>(c->arena[s]);
     char *dg = dv + align_up(nv * bs);
     char *dout = dg + align_up(ng * bs);
+    if (keep) {  // upload straight into the persistent copies: the next backward call reads them from there
+      dv = static_cast<char *>(c->keep_vol) + b0 * nv;
+      dg = static_cast<char *>(c->keep_grid) + b0 * ng;
+    }
     cudaStream_t st = c->stream[s];
     cudaError_t e;
     if ((e = cudaMemcpyAsync(dv, static_cast<const char *>(vol->data) + b0 * nv, nb * nv, cudaMemcpyHostToDevice, st)) !=
@@ -183,6 +226,12 @@ int volstn_b200_host_sampler_forward(volstn_host_ctx *c, int dtype, int G, const
     }
   }
   const int rs = sync_all(c);
+  if (keep && rc == VOLSTN_OK && rs == VOLSTN_OK) {
+    c->keep_valid = true;
+    c->keep_dtype = dtype;
+    c->keep_vol_key = *vol;
+    c->keep_grid_key = *grid;
+  }
   return rc ? rc : rs;
 }
 
@@ -216,6 +265,9 @@ int volstn_b200_host_sampler_backward(volstn_host_ctx *c, int dtype, int G, cons
   const size_t need =
       align_up(nv * bs) + align_up(ng * bs) + align_up(no * bs) + align_up(ngv * bs) + align_up(ngg * bs);
   const bool upload_gv = !og && !(flags & VOLSTN_BWD_ZERO_GRADVOL);  // accumulate semantics of the reference
+  const bool reuse = (flags & VOLSTN_HOST_REUSE_INPUTS) && c->keep_valid && c->keep_dtype == dtype &&
+                     same_desc(c->keep_vol_key, *vol) && same_desc(c->keep_grid_key, *grid);
+  c->keep_valid = false;  // one forward, one backward
   int rc = VOLSTN_OK;
   int slice = 0;
   for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
@@ -233,8 +285,13 @@ int volstn_b200_host_sampler_backward(volstn_host_ctx *c, int dtype, int G, cons
       if (e == cudaSuccess)
         e = cudaMemcpyAsync(dst, static_cast<const char *>(t->data) + b0 * per, nb * per, cudaMemcpyHostToDevice, st);
     };
-    h2d(dv, vol, nv);
-    h2d(dg, grid, ng);
+    if (reuse) {
+      dv = static_cast<char *>(c->keep_vol) + b0 * nv;
+      dg = static_cast<char *>(c->keep_grid) + b0 * ng;
+    } else {
+      h2d(dv, vol, nv);
+      h2d(dg, grid, ng);
+    }
     h2d(dgo, gradOut, no);
     if (upload_gv) h2d(dgv, gradVol, nv);
     if (e != cudaSuccess) {

@@ -128,10 +128,16 @@ class BilinearSamplerVolumetric(Module):
       onlyGrid    skip gradInput[1]  -- the reference's disabled onlyGrid switch (...c:594, ...cu:1079)
       onlyVolume  skip gradInput[2]
       algo / vpt  kernel variant selection for benchmarking (see include/volstn_b200.h)
+      reuseForwardInputs  host tensors only: updateGradInput re-uses the device copies updateOutput made of
+                  the same (pointer, shape) volume and grid instead of uploading them again -- nn.Module's
+                  contract (backward follows forward on the same input); set False if you mutate the
+                  inputs in place between the two calls
     """
 
-    def __init__(self, gridWidth: int = 4, onlyGrid: bool = False, onlyVolume: bool = False, algo: int = 0, vpt: int = 0):
+    def __init__(self, gridWidth: int = 4, onlyGrid: bool = False, onlyVolume: bool = False, algo: int = 0, vpt: int = 0,
+                 reuseForwardInputs: bool = True):
         super().__init__()
+        self.reuseForwardInputs = reuseForwardInputs
         self.gradInput = []  # lua:23  self.gradInput = {}
         assert gridWidth in (3, 4)
         self.gridWidth = gridWidth
@@ -182,7 +188,8 @@ class BilinearSamplerVolumetric(Module):
         else:
             g = grids if grids.is_contiguous() else grids.contiguous()
             dg = _desc(g)
-            rc = lib.volstn_b200_host_sampler_forward(_host_ctx(), dt, self.gridWidth, dv, dg, do, self._flags())
+            hf = self._flags() | (_abi.HOST_KEEP_INPUTS if self.reuseForwardInputs else 0)
+            rc = lib.volstn_b200_host_sampler_forward(_host_ctx(), dt, self.gridWidth, dv, dg, do, hf)
         _abi.check(rc, "BilinearSamplerVolumetric_updateOutput")
         self.output = out[0] if _inputImages.dim() == 4 else out
         return self.output
@@ -232,6 +239,8 @@ class BilinearSamplerVolumetric(Module):
         else:
             g = grids if grids.is_contiguous() else grids.contiguous()
             go = gradOutput if gradOutput.is_contiguous() else gradOutput.contiguous()
+            if self.reuseForwardInputs:
+                flags |= _abi.HOST_REUSE_INPUTS
             rc = lib.volstn_b200_host_sampler_backward(_host_ctx(), dt, self.gridWidth, _desc(inputImages), _desc(g),
                                                        _desc(gradInputImages), _desc(gradGrids), _desc(go), flags)
         _abi.check(rc, "BilinearSamplerVolumetric_updateGradInput")

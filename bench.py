@@ -351,11 +351,13 @@ def run_ours(a):
             if distributed:
                 e2e_s = shard.max_over_ranks(e2e_s, device="cuda")
             esz = 4
-            h2d = (vol_h.numel() + grid_h.numel()) * esz + (vol_h.numel() + grid_h.numel() + go_h.numel()) * esz
+            # forward uploads volume + grid; backward re-uses those device copies (nn.Module contract: backward
+            # follows forward on the same input, VOLSTN_HOST_REUSE_INPUTS) and uploads only gradOut
+            h2d = (vol_h.numel() + grid_h.numel()) * esz + go_h.numel() * esz
             d2h = (go_h.numel() + vol_h.numel() + grid_h.numel()) * esz
             e2e = {"value": V * n_gpus / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                   "path": "volstn_b200_host_sampler_forward/backward: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors"}
+                   "path": "volstn_b200_host_sampler_forward/backward: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors; backward re-uses the forward call's device copies of volume and grid"}
     clocks = sampler.summary()
 
     peak, peak_src = measured_peak()

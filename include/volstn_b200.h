@@ -66,6 +66,13 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_BWD_ZERO_GRADVOL 0x4u  /* zero-fill gradVol inside the call (replaces the Lua :zero() of
                                          BilinearSamplerVolumetric.lua:103); without it gradVol is
                                          ACCUMULATED into, exactly like the reference                       */
+/* HOST entry points only: keep device copies of the forward call's volume and grid in the context
+ * (KEEP, forward) and let the next backward call on the SAME host tensors skip their upload (REUSE,
+ * backward).  Legal under nn.Module's contract -- updateGradInput(input, gradOutput) presumes
+ * updateOutput(input) ran before with the same input -- and worth 320 of the 704 MB a 64^3 x 64 step
+ * uploads.  Matched by host pointer, shape, strides and dtype; ignored when they differ. */
+#define VOLSTN_HOST_KEEP_INPUTS 0x8u
+#define VOLSTN_HOST_REUSE_INPUTS 0x10u
 /* algorithm selection (bits 8..11), 0 = automatic.  Results are identical up to the summation
  * order of gradVol; exposed so that bench.py / profiles can time each variant. */
 #define VOLSTN_ALGO_SHIFT 8

@@ -60,3 +60,34 @@ def test_host_gridgen_and_cumsum():
     c = vnn.Cumsum()
     assert bits_equal(c.updateOutput(torch.from_numpy(x)).numpy(), oracle.cumsum_forward(x))
     assert bits_equal(c.updateGradInput(torch.from_numpy(x), torch.from_numpy(x)).numpy(), oracle.cumsum_backward(x))
+
+
+def test_host_backward_reuses_forward_inputs():
+    """VOLSTN_HOST_KEEP_INPUTS / _REUSE_INPUTS: the backward call skips the upload of volume and grid when it
+    follows a forward call on the same host tensors (nn.Module's contract); any other tensor falls back."""
+    rng = np.random.default_rng(9)
+    B, N, C = 9, 12, 2
+    vol = torch.from_numpy(synth.volume("v1", B, N, N, N, C, rng)).pin_memory()
+    grid = torch.from_numpy(synth.grid("g4", B, N, N, N, rng)).pin_memory()
+    go = torch.from_numpy(synth.grad_output(B, N, N, N, C, rng)).pin_memory()
+    rgv, rgg = oracle.sampler_backward(vol.numpy(), grid.numpy(), go.numpy())
+    m = vnn.BilinearSamplerVolumetric()          # reuseForwardInputs=True by default
+    m.updateOutput([vol, grid])
+    gv, gg = m.updateGradInput([vol, grid], go)
+    assert bits_equal(gg.numpy(), rgg) and max_rel(gv.numpy(), rgv) <= 1e-4
+    # a second backward without a forward in between must not reuse anything stale: change the grid in place
+    grid2 = grid.clone().pin_memory()
+    grid2[..., :3] *= 0.5
+    rgv2, rgg2 = oracle.sampler_backward(vol.numpy(), grid2.numpy(), go.numpy())
+    gv2, gg2 = m.updateGradInput([vol, grid2], go)           # different tensor -> uploaded
+    assert bits_equal(gg2.numpy(), rgg2) and max_rel(gv2.numpy(), rgv2) <= 1e-4
+    # forward on (vol, grid), backward on (vol, grid2): key mismatch -> falls back to uploading
+    m.updateOutput([vol, grid])
+    gv3, gg3 = m.updateGradInput([vol, grid2], go)
+    assert bits_equal(gg3.numpy(), rgg2)
+    # opting out re-uploads even for identical tensors (inputs mutated in place between the calls)
+    m2 = vnn.BilinearSamplerVolumetric(reuseForwardInputs=False)
+    m2.updateOutput([vol, grid])
+    grid[..., :3] *= 0.5                                       # in-place edit after forward
+    gv4, gg4 = m2.updateGradInput([vol, grid], go)
+    assert bits_equal(gg4.numpy(), rgg2)
