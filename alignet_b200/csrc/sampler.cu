@@ -604,7 +604,6 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
     if (packed_ok(G, vol, {grid, out})) {
-      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C)) return launch_fwd_tile(a, G, st);
       const int vpt = pick_vpt(flags, a.C, a.n);
       return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
     }
@@ -661,8 +660,8 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
     if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
-      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && tile_supported(a.C))
-        return launch_bwd_tile(a, G, og, ov, st);
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
+        return launch_bwd_tile(a, G, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
       if (vpt != 1 && vpt != 2) vpt = 2;
       return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st)

@@ -455,9 +455,8 @@ __device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a
   }
 }
 
-// brick-tiled kernels (sampler_tile.cu): packed float tensors, C <= 4
-bool tile_supported(int C);
-int launch_fwd_tile(const SamplerArgs<float> &a, int G, cudaStream_t st);
-int launch_bwd_tile(const SamplerArgs<float> &a, int G, bool only_grid, bool only_vol, cudaStream_t st);
+// shared-memory privatised backward (sampler_tile.cu): packed float tensors, C in {1, 2, 4}, 16-byte rows
+bool tile_supported(const SamplerArgs<float> &a);
+int launch_bwd_tile(const SamplerArgs<float> &a, int G, bool only_vol, cudaStream_t st);
 
 }  // namespace volstn
