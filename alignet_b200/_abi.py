@@ -20,7 +20,7 @@ BWD_ONLY_VOLUME = 0x2
 BWD_ZERO_GRADVOL = 0x4
 HOST_KEEP_INPUTS = 0x8
 HOST_REUSE_INPUTS = 0x10
-ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR = 0x000, 0x100, 0x200, 0x300
+ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR, ALGO_QUAD = 0x000, 0x100, 0x200, 0x300, 0x400
 VPT_SHIFT = 12
 
 

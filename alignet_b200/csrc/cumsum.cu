@@ -49,11 +49,24 @@ __global__ void __launch_bounds__(kCSThreads) k_cumsum(const CumsumArgs a) {
       const long long b = ln / lines_per_sample, r = ln % lines_per_sample;
       const long long o = r / inner, i = r % inner;
       const long long base = (b * a.N + ch) * a.S + o * L * inner + i;
+      // the loads of a line are independent: issue eight before the first (ordered) addition, otherwise
+      // every step of the scan pays a full memory round trip (9 us for a 384 KB cage, profiles/r01_aux*)
       double acc = 0.0;
-      for (long long k = 0; k < L; k++) {
-        const long long p = base + (REVERSE ? (L - 1 - k) : k) * inner;
-        acc += (double)in[p];
-        out[p] = (real)acc;
+      for (long long k0 = 0; k0 < L; k0 += 8) {
+        real v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const long long k = k0 + q;
+          v[q] = k < L ? in[base + (REVERSE ? (L - 1 - k) : k) * inner] : real(0);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const long long k = k0 + q;
+          if (k < L) {
+            acc += (double)v[q];
+            out[base + (REVERSE ? (L - 1 - k) : k) * inner] = (real)acc;
+          }
+        }
       }
     }
     return;

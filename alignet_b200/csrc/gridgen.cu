@@ -108,26 +108,40 @@ __global__ void __launch_bounds__(kGGThreads) k_gridgen_bwd_partial(const real *
 #pragma unroll
   for (int i = 0; i < 16; i++) acc[i] = real(0);
   const real *gb = gg + (long long)b * rows * W * 4;
-  for (; r < r_end; r++) {
-    const int y = (int)(r % H), z = (int)(r / H);
-    const real zn = tz[z], yn = ty[y];
-    const real *grow = gb + r * (long long)W * 4;
+  // Two rows per trip with all their loads issued before the first multiply-add: the accumulators are the
+  // only loop-carried state, so this doubles the bytes each warp keeps in flight.
+  auto accumulate = [&](const real (&g)[4], real zn, real yn, real xn) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      acc[i * 4 + 0] = fma(g[i], zn, acc[i * 4 + 0]);
+      acc[i * 4 + 1] = fma(g[i], yn, acc[i * 4 + 1]);
+      acc[i * 4 + 2] = fma(g[i], xn, acc[i * 4 + 2]);
+      acc[i * 4 + 3] += g[i];
+    }
+  };
+  auto load4 = [&](const real *p, real (&g)[4]) {
+    if constexpr (sizeof(real) == 4) {
+      const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(p));
+      g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+    } else {
+      const double4 v = *reinterpret_cast<const double4 *>(p);
+      g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+    }
+  };
+  constexpr int kRowsPerTrip = 4;
+  for (; r < r_end; r += kRowsPerTrip) {
     for (int x = lane; x < W; x += 32) {
-      real g[4];
-      if constexpr (sizeof(real) == 4) {
-        const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(grow + (long long)x * 4));
-        g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
-      } else {
-        const double4 v = *reinterpret_cast<const double4 *>(grow + (long long)x * 4);
-        g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
-      }
+      real g[kRowsPerTrip][4];
+#pragma unroll
+      for (int q = 0; q < kRowsPerTrip; q++)
+        if (r + q < r_end) load4(gb + ((r + q) * (long long)W + x) * 4, g[q]);
       const real xn = tx[x];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        acc[i * 4 + 0] = fma(g[i], zn, acc[i * 4 + 0]);
-        acc[i * 4 + 1] = fma(g[i], yn, acc[i * 4 + 1]);
-        acc[i * 4 + 2] = fma(g[i], xn, acc[i * 4 + 2]);
-        acc[i * 4 + 3] += g[i];
+      for (int q = 0; q < kRowsPerTrip; q++) {
+        if (r + q < r_end) {
+          const int y = (int)((r + q) % H), z = (int)((r + q) / H);
+          accumulate(g[q], tz[z], ty[y], xn);
+        }
       }
     }
   }
@@ -152,16 +166,25 @@ __global__ void __launch_bounds__(kGGThreads) k_gridgen_bwd_partial(const real *
 template <typename real>
 __global__ void k_gridgen_bwd_final(const double *__restrict__ partial, real *__restrict__ gradT, int nblk) {
   const int b = blockIdx.x, e = threadIdx.x;  // 16 threads
+  // loads issued eight at a time (they are independent; only the additions are ordered)
   double v = 0.0;
-  for (int k = 0; k < nblk; k++) v += partial[((long long)b * nblk + k) * 16 + e];
+  int k = 0;
+  for (; k + 8 <= nblk; k += 8) {
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) t[q] = partial[((long long)b * nblk + k + q) * 16 + e];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v += t[q];
+  }
+  for (; k < nblk; k++) v += partial[((long long)b * nblk + k) * 16 + e];
   gradT[(long long)b * 16 + e] = (real)v;
 }
 
 namespace {
 int bwd_blocks_per_sample(int64_t B, int64_t D, int64_t H, int *rows_per_warp) {
   const int64_t rows = D * H;
-  // aim for ~4 waves of 148 SMs x 8 CTAs over the whole batch, at least 4 rows per warp
-  int64_t want_blocks = (int64_t)kSMs * 8 * 4 / (B > 0 ? B : 1);
+  // aim for ~4 waves of 148 SMs x 3 CTAs (80 registers) over the whole batch, at least 4 rows per warp
+  int64_t want_blocks = (int64_t)kSMs * 3 * 4 / (B > 0 ? B : 1);
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpw = (rows + want_blocks * kGGWarps - 1) / (want_blocks * kGGWarps);
   if (rpw < 4) rpw = 4;

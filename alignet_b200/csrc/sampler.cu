@@ -126,8 +126,12 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
 #pragma unroll
         for (int v = 0; v < VPT; v++) {
           const unsigned j = j0 + v * kThreads;
-          voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1>(a, s[v], vb, gv_delta, sD, sH, go[v],
-                                                                 ggb + (size_t)j * G, j < n);
+          if (a.quad)
+            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1, true>(a, s[v], vb, gv_delta, sD, sH, go[v],
+                                                                         ggb + (size_t)j * G, j < n);
+          else
+            voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1, false>(a, s[v], vb, gv_delta, sD, sH, go[v],
+                                                                          ggb + (size_t)j * G, j < n);
         }
       } else if (__all_sync(0xffffffffu, tier >= 1)) {
 #pragma unroll
@@ -402,6 +406,7 @@ void fill_fast(SamplerArgs<real> &a) {
   a.fneg = 0;
   a.border_ok = 0;
   a.no_pair = 1;
+  a.quad = 0;
   a.one = 1.0f;
   if constexpr (sizeof(real) == 4) {
     if (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) {
@@ -660,6 +665,8 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
     if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
+      a.quad = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_QUAD && !og && a.C == 1 && a.iW % 4 == 0 &&
+                reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0) ? 1 : 0;
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
         return launch_bwd_tile(a, G, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);

@@ -33,6 +33,7 @@ struct SamplerArgs {
   unsigned n32, vs32;
   int border_ok;  // 0 disables the border tier (VOLSTN_DEBUG_NO_BORDER, A/B timing only)
   float one;      // 1.0f, opaque to the optimiser (sampler_pair.cuh::P2)
+  int quad;       // backward fast tier, C = 1: 16-byte vector reductions on aligned quads (VOLSTN_ALGO_QUAD)
   int no_pair;    // host only: use the scalar VPT = 2 kernels instead of the FADD2/FMUL2 pair kernels
 };
 
@@ -364,7 +365,7 @@ __device__ __forceinline__ void voxel_forward_packed(const SamplerArgs<real> &a,
 // go[] = gradOut of this voxel (already loaded).  gv_delta = gradVol sample base - volume sample base
 // in elements (both tensors are packed with identical strides), so corner k of gradVol is
 // rows.corner(k) + gv_delta.
-template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL, int MODE>
+template <typename real, int CT, int G, bool ONLY_GRID, bool ONLY_VOL, int MODE, bool QUAD = false>
 __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, const VoxelSetup<real> &s,
                                                   const real *__restrict__ vb, long long gv_delta, int sD, int sH,
                                                   const real (&go)[CT], real *__restrict__ ggp, bool valid = true) {
@@ -401,13 +402,34 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
     // reduction sector-ops with the identity field, same run time -- the kernel is then issue-bound) and
     // merging x-adjacent contributions across lanes with shuffles (the identity grid's coordinates are one
     // ulp below an integer 36 % of the time, so only ~30 % of the neighbours line up).
+    if constexpr (QUAD && FAST && CT == 1 && sizeof(real) == 4) {
+      // VOLSTN_ALGO_QUAD: the x0 / x0+1 pair of a row goes out as ONE 16-byte vector reduction on the
+      // aligned quad that contains x0 (zeros in the unused slots; a second scalar reduction only when x0
+      // is the last cell of its quad).  With a sheared field every lane is its own L2 sector-op, so this is
+      // 5 instead of 8 per voxel.  Needs 16-byte aligned rows (W % 4 == 0): the host checks.
+      const unsigned q = (unsigned)(reinterpret_cast<uintptr_t>(rows.p[0] + gv_delta) >> 2) & 3u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (valid && (FAST || s.in(k))) {
-        real r[CT];
+      for (int r = 0; r < 4; r++) {
+        const float lo = E::mul(cw[2 * r], go[0]), hi = E::mul(cw[2 * r + 1], go[0]);  // ...c:737
+        float *p = const_cast<float *>(rows.p[r]) + gv_delta - q;
+        const float vx = q == 0 ? lo : 0.f;
+        const float vy = q == 0 ? hi : (q == 1 ? lo : 0.f);
+        const float vz = q == 1 ? hi : (q == 2 ? lo : 0.f);
+        const float vw = q == 2 ? hi : (q == 3 ? lo : 0.f);
+        if (valid) {
+          red_add4(p, vx, vy, vz, vw);
+          if (q == 3) red_add(p + 4, hi);
+        }
+      }
+    } else {
 #pragma unroll
-        for (int t = 0; t < CT; t++) r[t] = E::mul(cw[k], go[t]);  // ...c:737
-        red_channels<real, CT>(const_cast<real *>(rows.template corner<CT>(k)) + gv_delta, r);
+      for (int k = 0; k < 8; k++) {
+        if (valid && (FAST || s.in(k))) {
+          real r[CT];
+#pragma unroll
+          for (int t = 0; t < CT; t++) r[t] = E::mul(cw[k], go[t]);  // ...c:737
+          red_channels<real, CT>(const_cast<real *>(rows.template corner<CT>(k)) + gv_delta, r);
+        }
       }
     }
   }

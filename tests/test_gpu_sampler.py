@@ -77,7 +77,7 @@ def test_float_parity_random(G, C, gk):
             out = cuda_forward(vol, grid, G, vpt=vpt, algo=algo)
             assert bits_equal(out, ref_out), (vpt, algo, describe_mismatch(out, ref_out))
     for vpt in (0, 1, 2):
-        for algo in (_abi.ALGO_AUTO, _abi.ALGO_DIRECT, _abi.ALGO_TILE, _abi.ALGO_PAIR):
+        for algo in (_abi.ALGO_AUTO, _abi.ALGO_DIRECT, _abi.ALGO_TILE, _abi.ALGO_PAIR, _abi.ALGO_QUAD):
             gv, gg = cuda_backward(vol, grid, go, G, vpt=vpt, algo=algo)
             assert bits_equal(gg, ref_gg), (vpt, algo, describe_mismatch(gg, ref_gg))
             assert_gradvol_close(gv, ref_gv, (vpt, algo))
