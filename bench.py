@@ -178,7 +178,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, batch_override=None):
@@ -426,7 +426,7 @@ def run_ours(a):
             line["aux_kernels"] = aux
         if sweep is not None:
             line["sweep"] = sweep
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -543,7 +543,22 @@ def run_sweep(a, torch, vnn, synth, _abi):
     return rows
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """print the one JSON line on the REAL stdout (see main)"""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner on
+    # stdout from C whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole
+    # run and the JSON line goes to a duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
