@@ -1,0 +1,48 @@
+"""torch.autograd glue over the nn mirror, so that the warp path can sit inside a PyTorch graph
+(used by tools/train_step.py, the ALIGNet-3D training-step configuration of BASELINE.json).
+
+Each Function calls the module's updateOutput in forward and updateGradInput in backward -- exactly
+the calls torch7's nn.Sequential makes (train.lua:123-126) -- so everything below is the C ABI.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import nn as vnn
+
+
+class _Sampler(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol, grid, module):
+        ctx.module = module
+        ctx.save_for_backward(vol, grid)
+        return module.updateOutput([vol, grid]).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        vol, grid = ctx.saved_tensors
+        gv, gg = ctx.module.updateGradInput([vol, grid], grad_out.contiguous())
+        return gv.clone(), gg.clone(), None
+
+
+class _Cumsum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module):
+        ctx.module = module
+        ctx.save_for_backward(x)
+        return module.updateOutput(x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        return ctx.module.updateGradInput(x, grad_out.contiguous()), None
+
+
+def bilinear_sampler_volumetric(vol: torch.Tensor, grid: torch.Tensor, module: vnn.BilinearSamplerVolumetric = None):
+    """out = sample(vol B x D x H x W x C, grid B x D x H x W x 4); differentiable in both arguments."""
+    return _Sampler.apply(vol, grid, module or vnn.BilinearSamplerVolumetric())
+
+
+def cumsum(x: torch.Tensor, module: vnn.Cumsum = None):
+    """nn.Cumsum on B x N x d1..dN; differentiable."""
+    return _Cumsum.apply(x, module or vnn.Cumsum())

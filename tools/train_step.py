@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""tools/train_step.py -- BASELINE.json config 3: an ALIGNet-3D training step at 64^3, global batch 64,
+random-init weights, batch-sharded over the ranks (SURVEY.md section 3.3 with the bracketed 3-D lift, section 8e).
+
+    python tools/train_step.py [--steps 10]                                   # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N ... tools/train_step.py
+
+The step is what train.lua:106-141 does per batch: CNN on the stacked source/target pair -> cage deltas
+-> Abs -> nn.Cumsum -> +beta -> cage up-sample (sampler, volume = cage, grid = identity field from
+nn.VolumetricGridGenerator) -> source warp (sampler) -> SmoothL1 -> backward -> Adam.  The CNN is
+the 3-D lift of models/alignet_2d.lua:33-57 in plain PyTorch (library code, NOT part of this repo's
+product); Cumsum, the grid generator and both samplers are this repo's kernels through the C ABI.
+The only collective is one NCCL all-reduce of the flattened CNN gradients (the warp path shards by
+sample and needs none).  Prints one JSON line: step time, samples/s, and the warp path's share.
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as tnn
+
+from alignet_b200 import autograd as vag, nn as vnn, shard, synth, _abi
+
+
+class WarpNet(tnn.Module):
+    """3-D lift of warpF + dNet (models/alignet_2d.lua:33-120), csz = 4 for 64^3 inputs."""
+
+    def __init__(self, csz=4):
+        super().__init__()
+        self.csz = csz
+        self.features = tnn.Sequential(
+            tnn.MaxPool3d(2), tnn.Conv3d(2, 20, 5), tnn.ReLU(True),
+            tnn.MaxPool3d(2), tnn.Conv3d(20, 20, 5), tnn.ReLU(True),
+            tnn.MaxPool3d(2), tnn.Conv3d(20, 20, 2), tnn.ReLU(True),
+            tnn.Conv3d(20, 20, 1), tnn.ReLU(True))                      # 64 -> 32 -> 28 -> 14 -> 10 -> 5 -> 4
+        self.fc = tnn.Sequential(tnn.Linear(20 * csz ** 3, 20), tnn.ReLU(True))
+        self.out = tnn.Linear(20, 3 * csz ** 3)
+        self.delta = 2.0 / (csz - 1)
+        with torch.no_grad():                                           # identity warp at init (lua:77-80,118-119)
+            self.out.weight.zero_()
+            self.out.bias.fill_(self.delta)
+        self.beta = tnn.Parameter(torch.tensor([-1.0 - self.delta]))    # learn_beta (lua:104-108)
+        self.cumsum = vnn.Cumsum()
+
+    def forward(self, pair):
+        B = pair.shape[0]
+        d = self.out(self.fc(self.features(pair).reshape(B, -1)))
+        d = d.abs().view(B, 3, self.csz, self.csz, self.csz)            # range_fct = abs (lua:84-92)
+        return vag.cumsum(d.contiguous(), self.cumsum) + self.beta      # nn.Cumsum -> + beta (lua:102-112)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--global-batch", type=int, default=64); ap.add_argument("--size", type=int, default=64)
+    a = ap.parse_args()
+    out_fd = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)                   # stdout = the JSON line only
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, csz = a.size, 4
+    lo, hi = shard.batch_slice(a.global_batch, world, rank)
+    B = hi - lo
+    torch.manual_seed(0)                                                # identical weights on every rank
+    net = WarpNet(csz).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    rng = np.random.default_rng(100 + rank)
+    src = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()          # B x D x H x W x 1
+    tgt = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()
+    pair = torch.stack([src[..., 0], tgt[..., 0]], dim=1).contiguous()              # B x 2 x D x H x W
+    gen = vnn.VolumetricGridGenerator(N, N, N)
+    field_i = gen.updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))         # constant, like fieldI (dataset_2d.lua:128)
+    up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
+    params = [p for p in net.parameters()]
+    crit = tnn.SmoothL1Loss()
+    ones = torch.ones((B, csz, csz, csz, 1), device="cuda")
+
+    def step(timers=None):
+        opt.zero_grad(set_to_none=True)
+        cage = net(pair)                                                            # B x 3 x csz^3
+        cage_vol = torch.cat([cage.permute(0, 2, 3, 4, 1), ones], dim=-1).contiguous()   # channels-last, 4th coord
+        if timers: timers[0].record()
+        field = vag.bilinear_sampler_volumetric(cage_vol, field_i, up)              # cage up-sample -> B x N^3 x 4
+        est = vag.bilinear_sampler_volumetric(src, field, warp)                     # source warp
+        if timers: timers[1].record()
+        loss = crit(est, tgt)
+        loss.backward()
+        if world > 1:                                                               # the one collective of the step
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat); flat /= world
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        opt.step()
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    n0 = _abi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (_abi.launch_count() - n0) // a.steps
+    if world > 1:
+        ms = shard.max_over_ranks(ms, device="cuda")
+    # warp-path forward share (two samplers) inside one more step
+    t = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    step(t); torch.cuda.synchronize()
+    warp_fwd_ms = t[0].elapsed_time(t[1])
+    nparam = sum(p.numel() for p in params)
+    if rank == 0:
+        print(json.dumps({"config": "ALIGNet-3D training step (BASELINE.json config 3)", "size": N, "global_batch": a.global_batch,
+                          "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "samples_per_s": a.global_batch / (ms * 1e-3),
+                          "voxels_per_s": a.global_batch * N ** 3 / (ms * 1e-3), "loss": float(loss.detach()),
+                          "warp_forward_ms": warp_fwd_ms, "volstn_kernels_per_step": int(launches),
+                          "allreduce_floats": nparam if world > 1 else 0, "scaling": "strong",
+                          "note": "CNN = plain PyTorch (3-D lift of models/alignet_2d.lua); Cumsum, grid generator and both samplers = this repo's kernels; one NCCL all-reduce of the CNN gradients per step"}),
+              file=out_fd, flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
