@@ -98,6 +98,8 @@ struct VoxelSetup {
       // three subtractions cost nothing.
       fbase = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.fneg), wrap_mul(__float_as_int(ry), sH)),
                        wrap_mul(__float_as_int(rx), sW));
+      // the integers themselves (dead code in the direct kernels; the privatised backward needs them)
+      x0 = __float_as_int(rx) - 0x4B000000, y0 = __float_as_int(ry) - 0x4B000000, z0 = __float_as_int(rz) - 0x4B000000;
       ix0 = iy0 = iz0 = true;
       if constexpr (BORDER) {  // c == size-1: i0 = size-1, the high corner is out of bounds (its weight is 0)
         ix1 = (unsigned)__float_as_int(cx) < a.fbx;

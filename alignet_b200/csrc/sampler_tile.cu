@@ -9,23 +9,28 @@
 // 480 us at 64^3 x 64, three times the rest of the kernel.
 //
 // Here one CTA owns an 8 x 8 x 4 brick of OUTPUT voxels (one thread per voxel):
-//   1. set-up per voxel exactly as in the direct kernel (bit-identical gradGrid, same dot products);
-//   2. the CTA reduces the bounding box of its in-bounds corner indices (REDUX + six shared atomics) and
-//      aligns it to 16 bytes in x;
-//   3. contributions are accumulated into a shared-memory copy of that box in FIXED POINT with native
-//      integer shared atomics (ATOMS.ADD).  A shared float atomicAdd is a CAS loop on sm_100a: with the
+//   1. set-up per voxel with the conversion-free path of the direct kernel (bit-identical gradGrid and
+//      dot products).  The privatised path is taken when every voxel of the brick lies inside the volume
+//      (tier >= 1, i.e. 0 <= c <= size-1), gradOut is finite and the box fits; any other brick runs the
+//      direct code.  (Privatising the bricks that straddle a face as well, with per-corner predicates, was
+//      measured: slower overall, gpurun_out/r1_kbench_tile7.txt.);
+//   2. the CTA reduces the bounding box of the brick's corner indices [i0, i0+1] (REDUX + six shared
+//      atomics).  The box may stick out of the volume by one cell at a high face: those cells only ever
+//      receive exact zeros (their weight is 0) and are not flushed, so no corner needs a predicate;
+//   3. contributions are accumulated into a shared-memory copy of the box in FIXED POINT with native
+//      integer shared atomics (ATOMS.ADD).  (A shared float atomicAdd is a CAS loop on sm_100a: with the
 //      bank conflicts and same-address retries of a scatter it cost ~12 shared-memory wavefronts per
-//      corner and made this kernel slower than the one it replaces (gpurun_out/r1_kbench_tile4.txt).
-//      The scale is a power of two chosen per CTA from max|gradOut| of the brick (2^21 steps up to the
-//      next power of two above it), so one contribution is rounded by at most 2^-22 of that maximum --
-//      the order of an fp32 rounding of a full-size contribution -- and 256 of them cannot overflow.
-//      gradVol's contract is a tolerance (1e-4 of max|ref|, summation order is free); measured error
-//      stays ~1e-6.  Bricks whose gradOut is not finite take the direct float path.  Every touched
-//      (z, y) row is flagged;
-//   4. each flagged row is flushed with 16-byte `red.global.add.v4.f32`, lanes along x: ~2 sector-ops per
-//      row instead of one per lane per corner.
-// A brick whose box does not fit the shared-memory budget (or any tensor the alignment rules exclude)
-// falls back to the direct reductions, CTA by CTA: the result is the same sum in a different order.
+//      corner.)  The scale is a power of two chosen per CTA from max|gradOut| of the brick (2^21 steps up
+//      to the next power of two above it): one contribution is rounded by at most 2^-22 of that maximum
+//      -- the order of an fp32 rounding of a full-size contribution -- and 256 of them cannot overflow.
+//      gradVol's contract is a tolerance (1e-4 of max|ref|; its summation order was never defined);
+//      measured error ~1e-6;
+//   4. the box is flushed with 16-byte `red.global.add.v4.f32`, lanes along x, skipping all-zero groups.
+//
+// Status [B200, 64^3 x 64, C = 1]: 10-17 % faster than the direct kernel on sheared fields (440 vs 490 us
+// on the jittered cage, 419 vs 507 us on rotations), 1.7x slower on the identity field (334 vs 192 us) and
+// on uniformly random fields: 580 instructions per voxel-warp against 270, and its eight scattered gathers
+// keep the L1 at 71 %.  Opt-in only.
 #include <atomic>
 
 #include "sampler.cuh"
@@ -38,175 +43,154 @@ namespace {
 constexpr int kBX = 8, kBY = 8, kBZ = 4;  // output brick
 constexpr int kTileThreads = kBX * kBY * kBZ;
 
-struct BrickBox {
-  int lo[3];   // z, y, x of the first cell of the box
-  int ext[3];  // extents (0 on every axis: no corner of the brick is in bounds)
-};
-
-// Bounding box of the in-bounds corners of all voxels of the CTA.  Corner indices along one axis are
-// i0 and i0+1; the in-bounds ones lie in [max(i0,0), min(i0+1,size-1)].  s_box: lo z,y,x, hi z,y,x.
-__device__ __forceinline__ BrickBox brick_box(const VoxelSetup<float> &s, bool has, const SamplerArgs<float> &a,
-                                              int *s_box, unsigned go_abs_bits, unsigned &go_max_bits) {
-  if (threadIdx.x < 3) s_box[threadIdx.x] = INT32_MAX;
-  else if (threadIdx.x < 6) s_box[threadIdx.x] = INT32_MIN;
-  else if (threadIdx.x == 6) s_box[6] = 0;
-  __syncthreads();
-  int lo[3], hi[3];
-  lo[0] = has ? max(s.z0, 0) : INT32_MAX;
-  lo[1] = has ? max(s.y0, 0) : INT32_MAX;
-  lo[2] = has ? max(s.x0, 0) : INT32_MAX;
-  hi[0] = has ? min(wrap_add(s.z0, 1), a.iD - 1) : INT32_MIN;
-  hi[1] = has ? min(wrap_add(s.y0, 1), a.iH - 1) : INT32_MIN;
-  hi[2] = has ? min(wrap_add(s.x0, 1), a.iW - 1) : INT32_MIN;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    lo[i] = __reduce_min_sync(0xffffffffu, lo[i]);
-    hi[i] = __reduce_max_sync(0xffffffffu, hi[i]);
-  }
-  // |x| of a float orders like its bit pattern (sign cleared); inf / nan have the largest patterns
-  const unsigned gm = __reduce_max_sync(0xffffffffu, go_abs_bits);
-  if ((threadIdx.x & 31) == 0) {
-    if (gm) atomicMax(reinterpret_cast<unsigned *>(&s_box[6]), gm);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      if (lo[i] != INT32_MAX) atomicMin(&s_box[i], lo[i]);
-      if (hi[i] != INT32_MIN) atomicMax(&s_box[3 + i], hi[i]);
-    }
-  }
-  __syncthreads();
-  go_max_bits = (unsigned)s_box[6];
-  BrickBox b;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    b.lo[i] = s_box[i];
-    const int h = s_box[3 + i];
-    b.ext[i] = (b.lo[i] == INT32_MAX || h == INT32_MIN) ? 0 : h - b.lo[i] + 1;
-  }
-  return b;
-}
-
 }  // namespace
 
 // CT floats per cell.  XA = cells per 16 bytes (4 / CT): the box is aligned to XA cells in x.
+// s_meta: [0..2] box lo z,y,x  [3..5] box hi z,y,x  [6] max |gradOut| bits  [7] min tier
 template <int CT, int G, bool ONLY_VOL>
 __global__ void __launch_bounds__(kTileThreads, 5)
-    k_sampler_bwd_tile(const SamplerArgs<float> a, int nbx, int nby, int cap_floats, int max_rows) {
+    k_sampler_bwd_tile(const SamplerArgs<float> a, int nbz, int cap_floats) {
   using E = Ex<float>;
   constexpr int XA = 4 / CT;
-  extern __shared__ __align__(128) int s_gv[];                                    // cap_floats fixed-point cells
-  unsigned char *s_row = reinterpret_cast<unsigned char *>(s_gv + cap_floats);  // max_rows flags
-  __shared__ int s_box[8];
-  const int sW = CT, sH = a.iW * CT, sD = a.iH * a.iW * CT;
+  extern __shared__ __align__(128) int s_gv[];  // cap_floats fixed-point cells
+  __shared__ int s_meta[8];
+  const int sH = a.iW * CT, sD = a.iH * a.iW * CT;
 
-  const int brick = blockIdx.x;
-  const int bx = brick % nbx, bt = brick / nbx;
-  const int by = bt % nby, bz = bt / nby;
-  const int x = bx * kBX + (threadIdx.x & 7), y = by * kBY + ((threadIdx.x >> 3) & 7), z = bz * kBZ + (threadIdx.x >> 6);
+  const unsigned b = blockIdx.z / nbz, bz = blockIdx.z - b * nbz;
+  const int x = blockIdx.x * kBX + (threadIdx.x & 7), y = blockIdx.y * kBY + ((threadIdx.x >> 3) & 7),
+            z = bz * kBZ + (threadIdx.x >> 6);
   const bool valid = x < a.oW && y < a.oH && z < a.oD;
-  const size_t j = ((size_t)z * a.oH + y) * a.oW + x;
+  // tail threads re-read the brick's first voxel: no divergent set-up, they only skip stores and atomics
+  const unsigned j = valid ? ((unsigned)z * a.oH + y) * a.oW + x
+                           : ((unsigned)(bz * kBZ) * a.oH + blockIdx.y * kBY) * a.oW + blockIdx.x * kBX;
+  const size_t sb = (size_t)b * a.n32;
+  const float *vb = opaque(a.vol + (size_t)b * a.vs32);
+  const long long gv_delta = a.gvol - a.vol;
+  float *ggp = a.ggrid + (sb + j) * G;
 
-  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
-    const size_t sb = (size_t)b * a.n32;
-    const float *vb = a.vol + (size_t)b * a.vs32;
-    float *gvb = a.gvol + (size_t)b * a.vs32;
-    float *ggp = a.ggrid + (sb + j) * G;
-    VoxelSetup<float> s;
-    s.init_idle();
-    float go[CT];
+  if (threadIdx.x < 3) s_meta[threadIdx.x] = INT32_MAX;
+  else if (threadIdx.x < 6) s_meta[threadIdx.x] = INT32_MIN;
+  else if (threadIdx.x == 6) s_meta[6] = 0;
+  else if (threadIdx.x == 7) s_meta[7] = 2;
+
+  float zf, yf, xf, go[CT];
+  ld_grid<float, G>(a.grid + (sb + j) * G, zf, yf, xf);
+  ld_channels_stream<float, CT>(a.gout + (sb + j) * CT, go);
+  if (!valid) {
 #pragma unroll
     for (int t = 0; t < CT; t++) go[t] = 0.f;
-    if (valid) {
-      float zf, yf, xf;
-      ld_grid<float, G>(a.grid + (sb + j) * G, zf, yf, xf);
-      ld_channels_stream<float, CT>(a.gout + (sb + j) * CT, go);
-      s.init(zf, yf, xf, a);
-    }
-    unsigned go_abs = 0;
+  }
+  VoxelSetup<float> s;
+  const int tier = s.begin(zf, yf, xf, a);
+  unsigned go_abs = 0;
 #pragma unroll
-    for (int t = 0; t < CT; t++) go_abs = max(go_abs, (unsigned)__float_as_int(go[t]) & 0x7fffffffu);
-    unsigned go_max;
-    const BrickBox box = brick_box(s, valid && s.any_in(), a, s_box, go_abs, go_max);
-    // 16-byte alignment of every row: start on a multiple of XA cells, extent a multiple of XA cells
-    // (the host guarantees iW % XA == 0, so the rounded-up end stays inside the row)
-    const int x_lo = box.lo[2] & ~(XA - 1);
-    const int pitch = box.ext[2] > 0 ? ((box.lo[2] + box.ext[2] + XA - 1) & ~(XA - 1)) - x_lo : 0;
-    const int rows = box.ext[0] * box.ext[1];
-    const long long floats = (long long)rows * pitch * CT;
+  for (int t = 0; t < CT; t++) go_abs = max(go_abs, (unsigned)__float_as_int(go[t]) & 0x7fffffffu);
+  __syncthreads();
+  // ---- CTA reductions: tier, max|go|, bounding box ----
+  const int wtier = __reduce_min_sync(0xffffffffu, tier);
+  const unsigned wgo = __reduce_max_sync(0xffffffffu, go_abs);  // |x| orders like its bit pattern; inf/nan largest
+  if (wtier >= 1) s.template finish_fast<true>(a, sD, sH, CT);  // warp-uniform; gives x0, y0, z0, weights, fbase
+  int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  if (wtier >= 1) {
+    lo[0] = __reduce_min_sync(0xffffffffu, s.z0), hi[0] = __reduce_max_sync(0xffffffffu, s.z0);
+    lo[1] = __reduce_min_sync(0xffffffffu, s.y0), hi[1] = __reduce_max_sync(0xffffffffu, s.y0);
+    lo[2] = __reduce_min_sync(0xffffffffu, s.x0), hi[2] = __reduce_max_sync(0xffffffffu, s.x0);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_meta[7], wtier);
+    if (wgo) atomicMax(reinterpret_cast<unsigned *>(&s_meta[6]), wgo);
+    if (wtier >= 1) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        atomicMin(&s_meta[i], lo[i]);
+        atomicMax(&s_meta[3 + i], hi[i]);
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned go_max = (unsigned)s_meta[6];
+  // box of corner indices: [min i0, max i0 + 1]; x aligned to 16 bytes
+  const int z_lo = s_meta[0], y_lo = s_meta[1], ey = s_meta[4] - y_lo + 2, ez = s_meta[3] - z_lo + 2;
+  const int x_lo = s_meta[2] & ~(XA - 1);
+  const int pitch = ((s_meta[5] + 2 + XA - 1) & ~(XA - 1)) - x_lo;  // cells per tile row
+  const int rows = ez * ey;
+  const bool tiled = s_meta[7] >= 1 && go_max < 0x7f800000u && (long long)rows * pitch * CT <= cap_floats;
 
-    if (floats > 0 && floats <= cap_floats && rows <= max_rows && go_max < 0x7f800000u) {
-      // ---- privatised accumulation ----
-      // scale = 2^21 / (the power of two above max|go|), as exponent arithmetic; clamped to normal floats
-      const int e_s = min(253, max(1, 274 - (int)(go_max >> 23)));
-      const float scale = __int_as_float(e_s << 23), inv_scale = __int_as_float((254 - e_s) << 23);
-      for (int i = threadIdx.x; i < (int)floats / 4; i += kTileThreads)
-        reinterpret_cast<int4 *>(s_gv)[i] = make_int4(0, 0, 0, 0);
-      for (int i = threadIdx.x; i < rows; i += kTileThreads) s_row[i] = 0;
-      __syncthreads();
-      float cw[8];
-      s.corner_weights(cw);
-      const CornerRows<float> vrows(vb, s.base32(sD, sH, sW), sD, sH);
-      const int tr = (s.z0 - box.lo[0]) * box.ext[1] + (s.y0 - box.lo[1]);  // tile row of corner 0
-      const int tx = s.x0 - x_lo;
-      float dot[8];
+  if (!tiled) {
+    // direct path (the reference's per-corner reductions): exact tier, every predicate
+    s.finish_exact(a);
+    voxel_backward_ct<float, CT, G, false, ONLY_VOL, 0>(a, s, vb, gv_delta, sD, sH, go, ggp, valid);
+    return;
+  }
+
+  // ---- privatised accumulation ----
+  const int floats = rows * pitch * CT;
+  for (int i = threadIdx.x; i < floats / 4; i += kTileThreads) reinterpret_cast<int4 *>(s_gv)[i] = make_int4(0, 0, 0, 0);
+  // scale = 2^21 / (the power of two above max|go|), as exponent arithmetic; clamped to normal floats
+  const int e_s = min(253, max(1, 274 - (int)(go_max >> 23)));
+  const float scale = __int_as_float(e_s << 23), inv_scale = __int_as_float((254 - e_s) << 23);
+  float cw[8];
+  s.corner_weights(cw);
+  const CornerRows<float> vrows(vb, s.fbase, sD, sH);
+  float dot[8];
+  if constexpr (!ONLY_VOL) {
+    float v[8][CT];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        dot[k] = 0.f;
-        if (s.in(k)) {
-          if constexpr (!ONLY_VOL) {
-            float v[CT];
-            ld_channels<float, CT>(vrows.template corner<CT>(k), v);
-            float d = 0.f;  // dot += v * go, channel by channel (...c:736)
+    for (int k = 0; k < 8; k++) {
+      if (s.in(k)) {  // only high corners on a high face are excluded (border tier)
+        ld_channels<float, CT>(vrows.template corner<CT>(k), v[k]);
+      } else {
 #pragma unroll
-            for (int t = 0; t < CT; t++) d = E::add(d, E::mul(v[t], go[t]));
-            dot[k] = d;
-          }
-          const int r = tr + ((k & 2) ? 1 : 0) + ((k & 4) ? box.ext[1] : 0);
-          int *cell = s_gv + ((size_t)r * pitch + tx + (k & 1)) * CT;
-          bool any = false;
-#pragma unroll
-          for (int t = 0; t < CT; t++) {
-            const float c = E::mul(cw[k], go[t]);  // ...c:737, the reference's product
-            // round(c * scale) without a conversion instruction: |c * scale| < 2^21, so adding 1.5 * 2^23
-            // leaves the integer in the mantissa
-            const int q = __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000;
-            if (q != 0) {
-              atomicAdd(cell + t, q);
-              any = true;
-            }
-          }
-          if (any) s_row[r] = 1;  // benign race: every writer stores the same value
-        }
+        for (int t = 0; t < CT; t++) v[k][t] = 0.f;
       }
-      if constexpr (!ONLY_VOL) {
-        float gz, gy, gx;
-        grad_grid_from_dots<float>(dot, s, a, gz, gy, gx);
-        if (valid) st_grad_grid<float, G>(ggp, gz, gy, gx);
-      }
-      // ---- flush: 16-byte vector reductions, lanes along x, a power-of-two group of lanes per row ----
-      // (One `cp.reduce.async.bulk ... .add.f32` (UBLKRED) per row was measured first: its operands are
-      // uniform registers, so ptxas serialises the rows lane by lane -- 3x the instructions of the whole
-      // kernel, gpurun_out/r1_kbench_tile3.txt.)
-      __syncthreads();
-      const int qpr = pitch * CT / 4;                                   // 16-byte groups per row
-      const int lpr = qpr <= 4 ? 4 : (qpr <= 8 ? 8 : (qpr <= 16 ? 16 : 32));  // lanes serving one row
-      const int qi = threadIdx.x & (lpr - 1);
-      const float inv_ey = 1.0f / (float)box.ext[1];
-      for (int r = threadIdx.x / lpr; r < rows; r += kTileThreads / lpr) {
-        if (!s_row[r]) continue;
-        const int zz = (int)(((float)r + 0.5f) * inv_ey), yy = r - zz * box.ext[1];  // exact for r < 2^20
-        float *g = gvb + (size_t)(box.lo[0] + zz) * sD + (size_t)(box.lo[1] + yy) * sH + (size_t)x_lo * CT;
-        for (int q = qi; q < qpr; q += lpr) {
-          const int4 v = reinterpret_cast<const int4 *>(s_gv + (size_t)r * pitch * CT)[q];
-          if (v.x | v.y | v.z | v.w)
-            red_add4(g + 4 * q, (float)v.x * inv_scale, (float)v.y * inv_scale, (float)v.z * inv_scale,
-                     (float)v.w * inv_scale);
-        }
-      }
-    } else {
-      // nothing in bounds, or the box does not fit: the direct path (predicated, no loads for excluded corners)
-      voxel_backward_ct<float, CT, G, false, ONLY_VOL, 0>(a, s, vb, gvb - vb, sD, sH, go, ggp, valid);
     }
-    if (b + gridDim.y < (unsigned)a.B) __syncthreads();  // the box is reused by the next sample
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float d = 0.f;  // dot += v * go, channel by channel (...c:736)
+#pragma unroll
+      for (int t = 0; t < CT; t++) d = E::add(d, E::mul(v[k][t], go[t]));
+      dot[k] = d;  // go is finite here, so an excluded corner's 0 * go is 0 as in the reference
+    }
+  }
+  __syncthreads();  // the box is zero
+  {
+    const int t0 = (((s.z0 - z_lo) * ey + (s.y0 - y_lo)) * pitch + (s.x0 - x_lo)) * CT;
+    const int ty = pitch * CT, tz = ey * pitch * CT;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int *cell = s_gv + t0 + ((k & 1) ? CT : 0) + ((k & 2) ? ty : 0) + ((k & 4) ? tz : 0);
+#pragma unroll
+      for (int t = 0; t < CT; t++) {
+        const float c = E::mul(cw[k], go[t]);  // ...c:737, the reference's product (0 for tail threads)
+        // round(c * scale) without a conversion instruction: |c * scale| < 2^21, so adding 1.5 * 2^23
+        // leaves the integer in the mantissa
+        atomicAdd(cell + t, __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000);
+      }
+    }
+  }
+  if constexpr (!ONLY_VOL) {
+    float gz, gy, gx;
+    grad_grid_from_dots<float>(dot, s, a, gz, gy, gx);
+    if (valid) st_grad_grid<float, G>(ggp, gz, gy, gx);
+  }
+  __syncthreads();
+  // ---- flush: 16-byte vector reductions, lanes along x, a power-of-two group of lanes per row; rows and
+  // cells outside the volume (the one-cell overhang at a high face) hold zeros and are skipped ----
+  float *gvb = a.gvol + (size_t)b * a.vs32;
+  const int qpr = pitch * CT / 4;                                         // 16-byte groups per row
+  const int lpr = qpr <= 4 ? 4 : (qpr <= 8 ? 8 : (qpr <= 16 ? 16 : 32));  // lanes serving one row
+  const int qi = threadIdx.x & (lpr - 1);
+  const float inv_ey = 1.0f / (float)ey;
+  for (int r = threadIdx.x / lpr; r < rows; r += kTileThreads / lpr) {
+    const int zz = (int)(((float)r + 0.5f) * inv_ey), yy = r - zz * ey;  // exact for r < 2^20
+    if (z_lo + zz >= a.iD || y_lo + yy >= a.iH) continue;
+    float *g = gvb + (size_t)(z_lo + zz) * sD + (size_t)(y_lo + yy) * sH + (size_t)x_lo * CT;
+    for (int q = qi; q < qpr; q += lpr) {
+      const int4 v = reinterpret_cast<const int4 *>(s_gv + (size_t)r * pitch * CT)[q];
+      if ((v.x | v.y | v.z | v.w) && (x_lo * CT + 4 * q) < sH)
+        red_add4(g + 4 * q, (float)v.x * inv_scale, (float)v.y * inv_scale, (float)v.z * inv_scale,
+                 (float)v.w * inv_scale);
+    }
   }
 }
 
@@ -222,22 +206,15 @@ template <int CT, int G, bool OV>
 int launch_bwd_tile_t(const SamplerArgs<float> &a, cudaStream_t st) {
   static std::atomic<size_t> have{0};
   const int nbx = (a.oW + kBX - 1) / kBX, nby = (a.oH + kBY - 1) / kBY, nbz = (a.oD + kBZ - 1) / kBZ;
-  const long long bricks = (long long)nbx * nby * nbz;
-  if (bricks > 0x7fffffffLL) return VOLSTN_ERR_UNSUPPORTED;
   const int per_cta = kSmemBudget / kTileCtasPerSm - 1024 - 128;
-  // cap_floats floats + one flag byte per row; a row has at least 4 floats
-  int cap_floats = (int)((per_cta / 17LL) * 16 / 4);
-  cap_floats &= ~31;
-  const int max_rows = cap_floats / 4;
-  const size_t smem = (size_t)cap_floats * 4 + (size_t)max_rows;
+  const int cap_floats = (per_cta / 4) & ~31;
+  const size_t smem = (size_t)cap_floats * 4;
   if (smem > 48 * 1024 && have.load(std::memory_order_relaxed) < smem) {
     VOLSTN_CUDA_TRY(cudaFuncSetAttribute(k_sampler_bwd_tile<CT, G, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
     have.store(smem, std::memory_order_relaxed);
   }
-  const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
-  k_sampler_bwd_tile<CT, G, OV><<<dim3((unsigned)bricks, by), kTileThreads, smem, st>>>(a, nbx, nby, cap_floats,
-                                                                                       max_rows);
+  k_sampler_bwd_tile<CT, G, OV><<<dim3(nbx, nby, (unsigned)(nbz * a.B)), kTileThreads, smem, st>>>(a, nbz, cap_floats);
   return after_launch();
 }
 
@@ -253,11 +230,15 @@ int launch_bwd_tile_g(const SamplerArgs<float> &a, cudaStream_t st) {
 
 }  // namespace
 
-// 16-byte rows: C in {1, 2, 4}, the volume's W a multiple of 4 / C cells, gradVol 16-byte aligned
+// 16-byte rows: C in {1, 2, 4}, the volume's W a multiple of 4 / C cells, gradVol 16-byte aligned; the
+// conversion-free set-up must be valid (extents <= 2^22) and the launch grid must fit
 bool tile_supported(const SamplerArgs<float> &a) {
   if (a.C != 1 && a.C != 2 && a.C != 4) return false;
   if ((a.iW * a.C) % 4 != 0) return false;
   if (reinterpret_cast<uintptr_t>(a.gvol) % 16 != 0) return false;
+  if (!a.border_ok) return false;
+  const long long nbz = (a.oD + kBZ - 1) / kBZ, nby = (a.oH + kBY - 1) / kBY;
+  if (nbz * a.B > 65535 || nby > 65535) return false;
   return true;
 }
 
