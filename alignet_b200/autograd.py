@@ -21,8 +21,19 @@ class _Sampler(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         vol, grid = ctx.saved_tensors
-        gv, gg = ctx.module.updateGradInput([vol, grid], grad_out.contiguous())
-        return gv.clone(), gg.clone(), None
+        # Selective backward: a product nobody asked for is not computed.  In ALIGNet
+        # training the source volume is data (models/alignet_2d.lua:23-24 wraps it in nn.Identity), so the
+        # source warp needs only gradGrid -- no zero-fill, no scatter -- and the cage up-sample's grid is the
+        # constant identity field, so it needs only gradVol.
+        need_vol, need_grid = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        m = ctx.module
+        saved = (m.onlyGrid, m.onlyVolume)
+        m.onlyGrid, m.onlyVolume = (not need_vol) and need_grid, need_vol and (not need_grid)
+        try:
+            gv, gg = m.updateGradInput([vol, grid], grad_out.contiguous())
+        finally:
+            m.onlyGrid, m.onlyVolume = saved
+        return (gv.clone() if need_vol else None), (gg.clone() if need_grid else None), None
 
 
 class _Cumsum(torch.autograd.Function):

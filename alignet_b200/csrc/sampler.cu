@@ -29,8 +29,9 @@ constexpr int kThreads = 256;
 // Tail lanes re-read the last voxel (no divergent set-up code) and only skip their stores.
 //
 // Measured and rejected on a B200 (gpurun_out/r1_kbench_pf.txt, r1_kbench_persist.txt): an L2 prefetch
-// of the grid one wave of CTAs ahead (no change) and a persistent, register-pipelined loop (64
-// registers, -30 %).
+// of the grid one wave of CTAs ahead (no change), a persistent, register-pipelined loop (64 registers,
+// -30 %) and a plain strided loop without prefetch (r1_kbench_loop.txt: 40 registers, -20 % even when the
+// launch covers the sample in one trip).
 // =============================================================================================
 template <typename real, int CT, int G, int VPT>
 __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerArgs<real> a) {

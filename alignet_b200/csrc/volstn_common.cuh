@@ -136,10 +136,6 @@ __device__ __forceinline__ float2 ld_stream_f2(const float2 *p) {
   asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
-// L2 prefetch: no register, no scoreboard.  Used to request the lines a CTA one wave AHEAD will stream,
-// so that HBM always has work queued while resident warps wait on their own gathers.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // streaming (evict-first) stores for write-once outputs.  Compiler intrinsics, NOT asm with a "memory"
 // clobber: a clobber is a compiler barrier, and the gathers of a thread's second voxel must be free to
 // move above the first voxel's store (these outputs are never read back inside a kernel).

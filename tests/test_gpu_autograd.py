@@ -36,3 +36,21 @@ def test_cumsum_function_matches_oracle_gradients():
     assert bits_equal(y.detach().cpu().numpy(), oracle.cumsum_forward(x))
     y.backward(torch.from_numpy(g).cuda())
     assert bits_equal(tx.grad.cpu().numpy(), oracle.cumsum_backward(g))
+
+
+def test_selective_backward_skips_unrequested_products():
+    """vol without requires_grad -> onlyGrid (no gradVol computed), grid without -> onlyVolume; values unchanged."""
+    rng = np.random.default_rng(23)
+    B, N = 2, 9
+    vol = synth.volume("v1", B, N, N, N, 1, rng)
+    grid = synth.grid("g5", B, N, N, N, rng)
+    go = synth.grad_output(B, N, N, N, 1, rng)
+    rgv, rgg = oracle.sampler_backward(vol, grid, go)
+    tv = torch.from_numpy(vol).cuda()
+    tg = torch.from_numpy(grid).cuda().requires_grad_(True)
+    vag.bilinear_sampler_volumetric(tv, tg).backward(torch.from_numpy(go).cuda())
+    assert tv.grad is None and bits_equal(tg.grad.cpu().numpy(), rgg)
+    tv2 = torch.from_numpy(vol).cuda().requires_grad_(True)
+    tg2 = torch.from_numpy(grid).cuda()
+    vag.bilinear_sampler_volumetric(tv2, tg2).backward(torch.from_numpy(go).cuda())
+    assert tg2.grad is None and max_rel(tv2.grad.cpu().numpy(), rgv) <= 1e-4
