@@ -7,6 +7,7 @@
 // upload of slice i+1, the kernels of slice i and the download of slice i-1 overlap (the B200 has
 // independent copy engines per direction).  The call returns after the last download.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -34,7 +35,15 @@ namespace volstn {
 namespace {
 
 constexpr size_t kAlign = 256;
-constexpr size_t kSliceTargetBytes = 48u << 20;  // per slice, all tensors together
+// per slice, all tensors together (VOLSTN_HOST_SLICE_MB overrides, for tuning)
+static size_t slice_target_bytes() {
+  static const size_t v = [] {
+    const char *e = getenv("VOLSTN_HOST_SLICE_MB");
+    const long long mb = e ? atoll(e) : 48;
+    return (size_t)(mb > 0 ? mb : 48) << 20;
+  }();
+  return v;
+}
 
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -72,7 +81,7 @@ int sync_all(volstn_host_ctx *c) {
 
 // samples per slice: ~kSliceTargetBytes, and enough slices to keep all slots busy
 int64_t slice_batch(int64_t B, size_t bytes_per_sample) {
-  int64_t bs = (int64_t)(kSliceTargetBytes / (bytes_per_sample ? bytes_per_sample : 1));
+  int64_t bs = (int64_t)(slice_target_bytes() / (bytes_per_sample ? bytes_per_sample : 1));
   const int64_t per_slot = (B + volstn_host_ctx::kSlots - 1) / volstn_host_ctx::kSlots;
   bs = std::min(bs, per_slot);
   return std::max<int64_t>(bs, 1);
