@@ -478,6 +478,28 @@ def run_aux(a, torch, vnn, synth, _abi, peak):
     res["cumsum_backward_us"] = timed(lambda: cs.updateGradInput(d, d)) * 1e3
     res["cumsum_note"] = f"B x 3 x {csz}^3 = {d.numel() * 4 / 1024:.0f} KiB: launch-latency bound, reported in us of one graph-replayed launch (the reference needs ~15 launches)"
 
+    # yardstick (NOT a parity oracle): ATen's 5-D grid_sample on the same problem -- same
+    # mathematics, but NCDHW layout, (x, y, z) grid order, a different un-normalise expression and no 4th
+    # grid component; forward + backward for both inputs.
+    try:
+        import torch.nn.functional as F
+        rngy = np.random.default_rng(3)
+        nb = min(B, 8)
+        vol_y = torch.from_numpy(synth.volume("v2", nb, N, N, N, 1, rngy)).cuda().repeat(B // nb, 1, 1, 1, 1)[..., 0].unsqueeze(1).contiguous().requires_grad_(True)
+        g_y = torch.from_numpy(synth.grid("g1", nb, N, N, N, rngy)[..., [2, 1, 0]].copy()).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous().requires_grad_(True)
+        go_y = torch.randn((B, 1, N, N, N), device="cuda")
+
+        def aten_step():
+            o = F.grid_sample(vol_y, g_y, mode="bilinear", padding_mode="zeros", align_corners=True)
+            torch.autograd.grad(o, (vol_y, g_y), go_y)
+
+        ms = timed(aten_step, reps=5, graph=False)
+        res["aten_grid_sample_yardstick"] = {"ms": ms, "voxels_per_s": V / (ms * 1e-3),
+                                             "note": "torch.nn.functional.grid_sample 5-D fwd+bwd, identity field, same 64^3 x batch; context only"}
+        del vol_y, g_y, go_y
+    except Exception as e:  # a yardstick must never break the bench
+        res["aten_grid_sample_yardstick"] = {"error": repr(e)[:200]}
+
     # BASELINE.json config 2: Cumsum integration + grid generator + cage up-sample + source warp, 32^3, batch 32
     Np, Bp = 32, 32
     rng = np.random.default_rng(5)

@@ -49,7 +49,7 @@ def _desc(a: np.ndarray) -> _Tensor5:
 
 def build(verbose: bool = False) -> None:
     """Compile the C restatement and, when /root/reference is present, the reference itself."""
-    r = subprocess.run(["make", "-C", HERE, "oracle", "ref"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", HERE, "oracle", "ref", "refcuda"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout, r.stderr)
     if r.returncode != 0:
@@ -250,3 +250,50 @@ def gridgen_backward(grad_grid: np.ndarray, accumulate=np.float64) -> np.ndarray
     base = gridgen_base(D, H, W, grad_grid.dtype).reshape(-1, 4)
     gt = np.einsum("bvi,vj->bij", grad_grid.reshape(B, -1, 4).astype(accumulate), base.astype(accumulate))
     return gt.astype(grad_grid.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's own CUDA kernels recompiled for sm_100a (oracle/ref_cuda_shim.cu): the GPU incumbent.
+# Arguments are torch CUDA tensors; launches on the current stream, like the reference (...cu:706).
+# --------------------------------------------------------------------------------------------
+REF_CUDA_SO = os.path.join(HERE, "_ref", "libcuvolstn_ref.so")
+
+
+class _CudaTensor5(ctypes.Structure):
+    _fields_ = [("size", ctypes.c_long * 5), ("stride", ctypes.c_long * 5), ("data", ctypes.c_void_p)]
+
+
+def have_ref_cuda() -> bool:
+    return os.path.exists(REF_CUDA_SO)
+
+
+_ref_cuda = None
+
+
+def _ref_cuda_lib():
+    global _ref_cuda
+    if _ref_cuda is None:
+        _ref_cuda = ctypes.CDLL(REF_CUDA_SO)
+        _ref_cuda.ref_cuda_call.restype = ctypes.c_int
+        _ref_cuda.ref_cuda_call.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return _ref_cuda
+
+
+def _cuda_desc(t):
+    d = _CudaTensor5()
+    d.data = t.data_ptr()
+    for i in range(5):
+        d.size[i] = t.size(i)
+        d.stride[i] = t.stride(i)
+    return d
+
+
+def ref_cuda_call(which: int, tensors) -> None:
+    """which: 0 Volumetric fwd (vol, grid, out) / 1 bwd (vol, grid, gradVol, gradGrid, gradOut); 2 / 3 the G = 3
+    twins.  The kernels require packed float tensors (...cu:606) and B * D <= 65535 (blockIdx.z, ...cu:702)."""
+    import torch
+    arr = (_CudaTensor5 * len(tensors))(*[_cuda_desc(t) for t in tensors])
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = _ref_cuda_lib().ref_cuda_call(which, len(tensors), ctypes.cast(arr, ctypes.c_void_p), st)
+    if rc != 0:
+        raise RuntimeError("reference CUDA launcher reported an error")
