@@ -318,3 +318,43 @@ def test_launch_counter_counts_our_kernels():
     rng = np.random.default_rng(1)
     cuda_forward(synth.volume("v1", 1, 4, 4, 4, 1, rng), synth.grid("g3", 1, 4, 4, 4, rng))
     assert _abi.launch_count() == n0 + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# the warp-voted tiers of the packed kernels (fast / border / exact) compute the same bits
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [1, 4])
+def test_tiers_are_bit_identical(C):
+    """Grids crafted so that whole warps land in each tier: strictly interior coordinates (fast), coordinates
+    exactly on the high faces (border), outside / non-finite coordinates (exact).  Every tier, every VPT and the
+    debug flags that force the slower tiers must give the oracle's bits."""
+    rng = np.random.default_rng(77)
+    B, D, H, W = 2, 6, 8, 64                                     # W = 64: two full warps per row
+    vol = synth.volume("v1", B, D, H, W, C, rng)
+    go = synth.grad_output(B, D, H, W, C, rng)
+    base = synth.grid("g1", B, D, H, W, rng)                     # identity: its last column sits ON the high face
+    grids = {
+        "interior": (base * np.float32(0.9)).astype(np.float32),                     # fast tier everywhere
+        "faces": base,                                                                # border tier for half the warps
+        "outside": (base * np.float32(1.3) + np.float32(0.05)).astype(np.float32),    # exact tier near the faces
+    }
+    nf = base.copy()
+    nf[0, 2, 3, 10, 0] = np.nan
+    nf[1, 1, 1, 40, 2] = np.inf
+    nf[1, 4, 6, 63, 1] = -np.inf
+    nf[0, 0, 0, 5, 2] = 3e9                                                           # beyond int32 after scaling
+    grids["nonfinite"] = nf
+    NO_FAST, NO_BORDER = 0x10000, 0x20000
+    for name, grid in grids.items():
+        ref_out = oracle.sampler_forward(vol, grid)
+        rgv, rgg = oracle.sampler_backward(vol, grid, go)
+        for vpt in (1, 2, 4):
+            for dbg in (0, NO_BORDER, NO_FAST):
+                m = vnn.BilinearSamplerVolumetric(vpt=vpt)
+                m._flags = (lambda v, d: (lambda: _abi.ALGO_DIRECT | _abi.VPT(v) | d))(vpt, dbg)
+                out = m.updateOutput([dev(vol), dev(grid)]).cpu().numpy()
+                assert bits_equal(out, ref_out), (name, vpt, hex(dbg), describe_mismatch(out, ref_out))
+                if vpt <= 2:
+                    gv, gg = m.updateGradInput([dev(vol), dev(grid)], dev(go))
+                    assert bits_equal(gg.cpu().numpy(), rgg), (name, vpt, hex(dbg), describe_mismatch(gg.cpu().numpy(), rgg))
+                    assert_gradvol_close(gv.cpu().numpy(), rgv, (name, vpt, hex(dbg)))
