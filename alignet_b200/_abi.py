@@ -20,7 +20,7 @@ BWD_ONLY_VOLUME = 0x2
 BWD_ZERO_GRADVOL = 0x4
 HOST_KEEP_INPUTS = 0x8
 HOST_REUSE_INPUTS = 0x10
-ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR, ALGO_QUAD = 0x000, 0x100, 0x200, 0x300, 0x400
+ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR, ALGO_QUAD, ALGO_ROW = 0x000, 0x100, 0x200, 0x300, 0x400, 0x500
 VPT_SHIFT = 12
 
 
@@ -47,6 +47,11 @@ SIGNATURES = {
     "volstn_b200_sampler_forward": (_i, [_i, _i, _P5, _P5, _P5, _u, _vp]),
     "volstn_b200_sampler_backward": (_i, [_i, _i, _P5, _P5, _P5, _P5, _P5, _u, _vp]),
     "volstn_b200_sampler_indices": (_i, [_i, _i, _pi64, _P5, _vp, _vp, _vp]),
+    "volstn_b200_affine_sampler_forward": (_i, [_i, _vp, _P5, _P5, _u, _vp]),
+    "volstn_b200_affine_sampler_backward": (_i, [_i, _vp, _P5, _P5, _vp, _P5, _vp, _sz, _u, _vp]),
+    "volstn_b200_affine_sampler_backward_workspace": (_sz, [_i64, _i64, _i64, _i64]),
+    "volstn_b200_cage_warp_forward": (_i, [_i, _vp, _pi64, _P5, _P5, _u, _vp]),
+    "volstn_b200_cage_warp_backward": (_i, [_i, _vp, _pi64, _P5, _P5, _vp, _P5, _u, _vp]),
     "volstn_b200_gridgen_forward": (_i, [_i, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "volstn_b200_gridgen_backward": (_i, [_i, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "volstn_b200_gridgen_backward_workspace": (_sz, [_i64, _i64, _i64, _i64]),

@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "sampler_pair.cuh"
+#include "volstn_internal.h"
 
 namespace volstn {
 
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_generic(const SamplerA
     const long long ooff = voxel_offset<real>(idx, a, a.os, b2);
     const real *g = a.grid + goff;
     VoxelSetup<real> s;
-    s.init(g[0], g[1], g[2], a);
+    s.init(g[0], g[a.gs4], g[2 * a.gs4], a);
     real cw[8];
     s.corner_weights(cw);
     const real *vb = a.vol + (long long)b * a.vs[0];
@@ -283,11 +284,11 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_generic(const SamplerA
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int k = (G == 4) ? order_xyz(j) : order_zxy(j);
-        const real v = s.in(k) ? vb[off[k] + t] : real(0);
+        const real v = s.in(k) ? vb[off[k] + t * a.vs4] : real(0);
         const real term = E::mul(cw[k], v);
         acc = (j == 0) ? term : E::add(acc, term);
       }
-      o[t] = acc;
+      o[t * a.os4] = acc;
     }
   }
 }
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_generic(const SamplerA
     const long long ggoff = voxel_offset<real>(idx, a, a.ggs, bx);
     const real *g = a.grid + goff;
     VoxelSetup<real> s;
-    s.init(g[0], g[1], g[2], a);
+    s.init(g[0], g[a.gs4], g[2 * a.gs4], a);
     real cw[8];
     s.corner_weights(cw);
     const real *vb = a.vol + (long long)b * a.vs[0];
@@ -321,12 +322,12 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_generic(const SamplerA
     }
     const real *gop = a.gout + ooff;
     for (int t = 0; t < a.C; t++) {
-      const real go = gop[t];
+      const real go = gop[t * a.os4];
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         if (s.in(k)) {
-          if constexpr (!ONLY_VOL) dot[k] = E::add(dot[k], E::mul(vb[off[k] + t], go));
-          if constexpr (!ONLY_GRID) red_add(gvb + goffs[k] + t, E::mul(cw[k], go));
+          if constexpr (!ONLY_VOL) dot[k] = E::add(dot[k], E::mul(vb[off[k] + t * a.vs4], go));
+          if constexpr (!ONLY_GRID) red_add(gvb + goffs[k] + t * a.gvs4, E::mul(cw[k], go));
         }
       }
     }
@@ -335,9 +336,9 @@ __global__ void __launch_bounds__(kThreads) k_sampler_bwd_generic(const SamplerA
       grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
       real *gg = a.ggrid + ggoff;
       gg[0] = gz;
-      gg[1] = gy;
-      gg[2] = gx;
-      if constexpr (G == 4) gg[3] = real(0);
+      gg[a.ggs4] = gy;
+      gg[2 * a.ggs4] = gx;
+      if constexpr (G == 4) gg[3 * a.ggs4] = real(0);
     }
   }
 }
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) k_sampler_indices(const SamplerArgs<
     int b;
     const real *g = a.grid + voxel_offset<real>(idx, a, a.gs, b);
     VoxelSetup<real> s;
-    s.init(g[0], g[1], g[2], a);
+    s.init(g[0], g[a.gs4], g[2 * a.gs4], a);
     idx_out[idx * 3 + 0] = s.z0;
     idx_out[idx * 3 + 1] = s.y0;
     idx_out[idx * 3 + 2] = s.x0;
@@ -380,8 +381,7 @@ int check_desc(const volstn_tensor5 *t) {
   if (!t) return VOLSTN_ERR_ARG;
   for (int i = 0; i < 5; i++)
     if (!fits_int(t->size[i])) return VOLSTN_ERR_ARG;
-  if (t->size[4] > 1 && t->stride[4] != 1) return VOLSTN_ERR_LAYOUT;
-  return VOLSTN_OK;
+  return VOLSTN_OK;  // any element strides: the packed kernels need contiguity (packed_ok), the others honour them
 }
 
 int64_t numel(const volstn_tensor5 *t) { return t->size[0] * t->size[1] * t->size[2] * t->size[3] * t->size[4]; }
@@ -446,6 +446,10 @@ void fill_common(SamplerArgs<real> &a, const volstn_tensor5 *vol, const volstn_t
     a.gvs[i] = 0;
     a.ggs[i] = 0;
   }
+  a.vs4 = vol->stride[4];
+  a.gs4 = grid->stride[4];
+  a.os4 = outlike->stride[4];
+  a.gvs4 = a.ggs4 = 1;
   a.dm1 = (real)(a.iD - 1);
   a.hm1 = (real)(a.iH - 1);
   a.wm1 = (real)(a.iW - 1);
@@ -609,10 +613,13 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
-    if (packed_ok(G, vol, {grid, out})) {
+    const bool force_row = (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW;
+    if (!force_row && packed_ok(G, vol, {grid, out})) {
       const int vpt = pick_vpt(flags, a.C, a.n);
       return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
     }
+    // strided or planar tensors (e.g. permuted views of B x C x D x H x W tensors): the row kernels
+    if ((rc = row_sampler_forward(G, vol, grid, out, flags, st)) != -1) return rc;
     return launch_fwd_generic<float>(a, G, st);
   }
   SamplerArgs<double> a;
@@ -643,7 +650,7 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
   }
   const size_t esz = dtype == VOLSTN_F32 ? 4 : 8;
   if (!og && (flags & VOLSTN_BWD_ZERO_GRADVOL) && numel(gradVol)) {
-    if (!is_contiguous(gradVol)) return VOLSTN_ERR_LAYOUT;
+    if (!desc_dense(gradVol)) return VOLSTN_ERR_LAYOUT;
     VOLSTN_CUDA_TRY(cudaMemsetAsync(gradVol->data, 0, (size_t)numel(gradVol) * esz, st));
   }
   if (numel(gradOut) == 0) return VOLSTN_OK;
@@ -657,15 +664,18 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     if (!og) {
       a.gvol = static_cast<float *>(gradVol->data);
       for (int i = 0; i < 4; i++) a.gvs[i] = gradVol->stride[i];
+      a.gvs4 = gradVol->stride[4];
     }
     if (!ov) {
       a.ggrid = static_cast<float *>(gradGrid->data);
       for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
+      a.ggs4 = gradGrid->stride[4];
     }
     if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
-    if (packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
+    const bool force_row = (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW;
+    if (!force_row && packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
       a.quad = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_QUAD && !og && a.C == 1 && a.iW % 4 == 0 &&
                 reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0) ? 1 : 0;
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
@@ -675,6 +685,7 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st)
                     : dispatch_bwd_packed<3>(a, og, ov, vpt, st);
     }
+    if ((rc = row_sampler_backward(G, vol, grid, gradVol, gradGrid, gradOut, og, ov, flags, st)) != -1) return rc;
     return launch_bwd_generic<float>(a, G, og, ov, st);
   }
   SamplerArgs<double> a;
@@ -683,10 +694,12 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
   if (!og) {
     a.gvol = static_cast<double *>(gradVol->data);
     for (int i = 0; i < 4; i++) a.gvs[i] = gradVol->stride[i];
+    a.gvs4 = gradVol->stride[4];
   }
   if (!ov) {
     a.ggrid = static_cast<double *>(gradGrid->data);
     for (int i = 0; i < 4; i++) a.ggs[i] = gradGrid->stride[i];
+    a.ggs4 = gradGrid->stride[4];
   }
   return launch_bwd_generic<double>(a, G, og, ov, st);
 }

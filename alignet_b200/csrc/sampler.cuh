@@ -35,6 +35,10 @@ struct SamplerArgs {
   float one;      // 1.0f, opaque to the optimiser (sampler_pair.cuh::P2)
   int quad;       // backward fast tier, C = 1: 16-byte vector reductions on aligned quads (VOLSTN_ALGO_QUAD)
   int no_pair;    // host only: use the scalar VPT = 2 kernels instead of the FADD2/FMUL2 pair kernels
+  // generic kernels only: element stride of the LAST dimension (channels / grid components) of every tensor.
+  // The reference assumes 1 (`+ t`, `+ 1`, `+ 2`: ...c:492-495, 556); honouring it lets a B x C x D x H x W
+  // tensor be passed as a permuted view instead of through a materialised nn.Transpose copy
+  long long vs4, gs4, os4, gvs4, ggs4;
 };
 
 // Everything that depends only on the grid element and the volume extents.

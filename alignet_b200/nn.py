@@ -29,7 +29,8 @@ import torch
 from . import _abi
 from ._abi import Tensor5
 
-__all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum"]
+__all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
+           "AffineSamplerVolumetric", "CageWarpVolumetric"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -128,6 +129,11 @@ class BilinearSamplerVolumetric(Module):
       onlyGrid    skip gradInput[1]  -- the reference's disabled onlyGrid switch (...c:594, ...cu:1079)
       onlyVolume  skip gradInput[2]
       algo / vpt  kernel variant selection for benchmarking (see include/volstn_b200.h)
+      layout      "BDHWC" (the Lua class: channels-last volume, ``... x 4`` grid) or "BCDHW": volume
+                  ``B x C x D x H x W``, grid ``B x G x D x H x W``, output ``B x C x oD x oH x oW`` -- the tensors the
+                  reference feeds through materialised ``nn.Transpose`` copies around the sampler
+                  (stn3dtorch/test.lua:17,21; models/alignet.lua:11,14,21).  The kernels read and write the
+                  channel-first tensors in place through permuted views; no copy is made (CUDA tensors only)
       reuseForwardInputs  host tensors only: updateGradInput re-uses the device copies updateOutput made of
                   the same (pointer, shape) volume and grid instead of uploading them again -- nn.Module's
                   contract (backward follows forward on the same input); set False if you mutate the
@@ -135,8 +141,10 @@ class BilinearSamplerVolumetric(Module):
     """
 
     def __init__(self, gridWidth: int = 4, onlyGrid: bool = False, onlyVolume: bool = False, algo: int = 0, vpt: int = 0,
-                 reuseForwardInputs: bool = True):
+                 reuseForwardInputs: bool = True, layout: str = "BDHWC"):
         super().__init__()
+        assert layout in ("BDHWC", "BCDHW")
+        self.layout = layout
         self.reuseForwardInputs = reuseForwardInputs
         self.gradInput = []  # lua:23  self.gradInput = {}
         assert gridWidth in (3, 4)
@@ -149,7 +157,8 @@ class BilinearSamplerVolumetric(Module):
     # lua:26-42
     def check(self, input, gradOutput=None):
         inputImages, grids = input[0], input[1]
-        assert inputImages.is_contiguous(), "Input images have to be contiguous"
+        if self.layout == "BDHWC":
+            assert inputImages.is_contiguous(), "Input images have to be contiguous"
         assert inputImages.dim() == 5
         assert grids.dim() == 5
         assert inputImages.size(0) == grids.size(0)  # batch
@@ -163,8 +172,57 @@ class BilinearSamplerVolumetric(Module):
     def _flags(self) -> int:
         return (self.algo & 0xF00) | _abi.VPT(self.vpt)
 
+    # the nn.Transpose pairs of the reference as views
+    @staticmethod
+    def _cl(t):
+        return t.permute(0, 2, 3, 4, 1)
+
+    @staticmethod
+    def _cf(t):
+        return t.permute(0, 4, 1, 2, 3)
+
+    def _updateOutput_cf(self, input):
+        vol, grid = input[0], input[1]
+        assert vol.is_cuda, "layout='BCDHW' is implemented for CUDA tensors"
+        assert vol.dim() == 5 and grid.dim() == 5 and vol.is_contiguous(), "Input images have to be contiguous"
+        v, g = self._cl(vol), self._cl(grid)
+        self.check([v, g])
+        _same_place(vol, grid)
+        out = torch.empty((vol.size(0), vol.size(1), grid.size(2), grid.size(3), grid.size(4)), dtype=vol.dtype, device=vol.device)
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_sampler_forward(_dtype_code(vol), self.gridWidth, _desc(v), _desc(g), _desc(self._cl(out)),
+                                                        self._flags(), _stream(vol))
+        _abi.check(rc, "BilinearSamplerVolumetric_updateOutput")
+        self.output = out
+        return out
+
+    def _updateGradInput_cf(self, input, gradOutput):
+        vol, grid = input[0], input[1]
+        v, g, go = self._cl(vol), self._cl(grid), self._cl(gradOutput)
+        self.check([v, g], go)
+        _same_place(vol, grid, gradOutput)
+        assert gradOutput.size(1) == vol.size(1)
+        gv, gg = torch.empty_like(vol), torch.empty_like(grid, memory_format=torch.contiguous_format)
+        flags = self._flags() | _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gv.zero_()
+        if self.onlyVolume:
+            flags |= _abi.BWD_ONLY_VOLUME
+            gg.zero_()
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_sampler_backward(_dtype_code(vol), self.gridWidth, _desc(v), _desc(g), _desc(self._cl(gv)),
+                                                         _desc(self._cl(gg)), _desc(go), flags, _stream(vol))
+        _abi.check(rc, "BilinearSamplerVolumetric_updateGradInput")
+        self.gradInput = [gv, gg]
+        return self.gradInput
+
     # lua:54-81
     def updateOutput(self, input):
+        if self.layout == "BCDHW":
+            return self._updateOutput_cf(input)
         _inputImages, _grids = input[0], input[1]
         if _inputImages.dim() == 4:
             inputImages, grids = _add_outer_dim(_inputImages), _add_outer_dim(_grids)
@@ -196,6 +254,8 @@ class BilinearSamplerVolumetric(Module):
 
     # lua:83-117
     def updateGradInput(self, _input, _gradOutput):
+        if self.layout == "BCDHW":
+            return self._updateGradInput_cf(_input, _gradOutput)
         _inputImages, _grids = _input[0], _input[1]
         if _inputImages.dim() == 4:
             inputImages, grids, gradOutput = (_add_outer_dim(_inputImages), _add_outer_dim(_grids),
@@ -395,3 +455,142 @@ class Cumsum(Module):
     def clearState(self):
         self._gradOutput = None  # Cumsum.lua:53-56
         return super().clearState()
+
+
+# ------------------------------------------------------------------------------------------------
+# fused modules: no Lua counterpart; each replaces a sub-graph of reference
+# modules and returns that sub-graph's values
+# ------------------------------------------------------------------------------------------------
+def _vol_view(t: torch.Tensor, layout: str) -> torch.Tensor:
+    return t if layout == "BDHWC" else t.permute(0, 2, 3, 4, 1)
+
+
+class AffineSamplerVolumetric(Module):
+    """``nn.ParallelTable():add(volume):add(nn.VolumetricGridGenerator(depth, height, width))`` followed by
+    ``nn.BilinearSamplerVolumetric()`` -- the *projector* of stn3dtorch/test.lua:15-25 and the loader-side affine
+    augmentation of dataset_2d.lua:285-311 -- as ONE kernel: the sampling grid ``T[b] . (zn, yn, xn, 1)`` is
+    formed in registers and never written (16 B/voxel saved in each direction, no B-replicated base grid).
+
+    ``updateOutput({volume, T})``, ``updateGradInput({volume, T}, gradOutput) -> {gradVolume, gradT}``.
+    Values are bit-identical to the two-module chain of this package (gradT: same deterministic reduction
+    design, compared within 1e-5 relative)."""
+
+    def __init__(self, depth: int, height: int, width: int, layout: str = "BDHWC", onlyGrid: bool = False):
+        super().__init__()
+        assert depth > 1 and height > 1 and width > 1  # VolumetricGridGenerator.lua:6-8
+        assert layout in ("BDHWC", "BCDHW")
+        self.depth, self.height, self.width, self.layout, self.onlyGrid = depth, height, width, layout, onlyGrid
+        self.gradInput = []
+
+    def _T(self, T):
+        T = T.view(1, 4, 4) if T.dim() == 2 else T
+        assert T.dim() == 3 and T.size(1) == 4 and T.size(2) == 4, "please input affine transform matrices (bx4x4)"
+        return T if T.is_contiguous() else T.contiguous()
+
+    def updateOutput(self, input):
+        vol, T = input[0], self._T(input[1])
+        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == T.size(0)
+        _same_place(vol, T)
+        v = _vol_view(vol, self.layout)
+        B, C = v.size(0), v.size(4)
+        shape = (B, self.depth, self.height, self.width, C) if self.layout == "BDHWC" else (B, C, self.depth, self.height, self.width)
+        out = torch.empty(shape, dtype=vol.dtype, device=vol.device)
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_affine_sampler_forward(_dtype_code(vol), T.data_ptr(), _desc(v),
+                                                               _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        _abi.check(rc, "AffineSamplerVolumetric_updateOutput")
+        self.output = out
+        return out
+
+    def updateGradInput(self, input, gradOutput):
+        vol, T = input[0], self._T(input[1])
+        _same_place(vol, T, gradOutput)
+        v, go = _vol_view(vol, self.layout), _vol_view(gradOutput, self.layout)
+        B = v.size(0)
+        assert tuple(go.shape) == (B, self.depth, self.height, self.width, v.size(4))
+        gv = torch.empty_like(vol)
+        gradT = torch.empty((B, 4, 4), dtype=vol.dtype, device=vol.device)
+        lib = _abi.lib()
+        ws_bytes = int(lib.volstn_b200_affine_sampler_backward_workspace(B, self.depth, self.height, self.width))
+        ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=vol.device)
+        flags = _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gv.zero_()
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = lib.volstn_b200_affine_sampler_backward(_dtype_code(vol), T.data_ptr(), _desc(v), _desc(_vol_view(gv, self.layout)),
+                                                         gradT.data_ptr(), _desc(go), ws.data_ptr(), ws.numel() * 8, flags,
+                                                         _stream(vol))
+        _abi.check(rc, "AffineSamplerVolumetric_updateGradInput")
+        self.gradInput = [gv, gradT[0] if input[1].dim() == 2 else gradT]
+        return self.gradInput
+
+
+class CageWarpVolumetric(Module):
+    """ALIGNet's warp sub-graph (models/alignet_2d.lua:136-147 with alignet.lua:4-39, lifted to 3-D) as ONE kernel:
+
+        cage  B x 3 x cD x cH x cW  (the output of nn.Cumsum + beta, models/alignet_2d.lua:104-115)
+          -> bilinearSampler()({cage, fieldI})      up-sample to the full-resolution field
+          -> bilinearSampler()({source, field})     warp the source
+
+    The cage lives in shared memory; the full-resolution field, the constant identity field ``fieldI`` and, in the
+    backward pass, the field's gradient never exist in HBM (128 of the chain's 148 B/voxel).
+
+    ``updateOutput({source, cage})``, ``updateGradInput({source, cage}, gradOutput) -> {gradSource, gradCage}``.
+    ``onlyGrid=True`` skips gradSource (the source is data behind nn.Identity, models/alignet_2d.lua:23-24)."""
+
+    def __init__(self, depth: Optional[int] = None, height: Optional[int] = None, width: Optional[int] = None,
+                 layout: str = "BDHWC", onlyGrid: bool = False):
+        super().__init__()
+        assert layout in ("BDHWC", "BCDHW")
+        self.depth, self.height, self.width, self.layout, self.onlyGrid = depth, height, width, layout, onlyGrid
+        self.gradInput = []
+
+    def _out_dims(self, v):
+        return (self.depth or v.size(1), self.height or v.size(2), self.width or v.size(3))
+
+    @staticmethod
+    def _cage(cage):
+        assert cage.dim() == 5 and cage.size(1) == 3, "cage must be B x 3 x cD x cH x cW"
+        return cage if cage.is_contiguous() else cage.contiguous()
+
+    def updateOutput(self, input):
+        vol, cage = input[0], self._cage(input[1])
+        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == cage.size(0)
+        _same_place(vol, cage)
+        v = _vol_view(vol, self.layout)
+        B, C = v.size(0), v.size(4)
+        d, h, w = self._out_dims(v)
+        out = torch.empty((B, d, h, w, C) if self.layout == "BDHWC" else (B, C, d, h, w), dtype=vol.dtype, device=vol.device)
+        dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_cage_warp_forward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                          _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        _abi.check(rc, "CageWarpVolumetric_updateOutput")
+        self.output = out
+        return out
+
+    def updateGradInput(self, input, gradOutput):
+        vol, cage = input[0], self._cage(input[1])
+        _same_place(vol, cage, gradOutput)
+        v, go = _vol_view(vol, self.layout), _vol_view(gradOutput, self.layout)
+        d, h, w = self._out_dims(v)
+        assert tuple(go.shape) == (v.size(0), d, h, w, v.size(4))
+        gv = torch.empty_like(vol)
+        gcage = torch.empty_like(cage)
+        dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
+        flags = _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gv.zero_()
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_cage_warp_backward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                           _desc(_vol_view(gv, self.layout)), gcage.data_ptr(), _desc(go), flags,
+                                                           _stream(vol))
+        _abi.check(rc, "CageWarpVolumetric_updateGradInput")
+        self.gradInput = [gv, gcage]
+        return self.gradInput

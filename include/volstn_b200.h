@@ -11,8 +11,11 @@
  * Conventions
  *  - plain C: pointers, sizes, element strides; no Torch / PyTorch types.
  *  - tensors are 5-D descriptors  B x D x H x W x {C | G}  exactly like the reference's
- *    THTensor (size[], stride[], data).  Strides are in ELEMENTS.  The last dimension must have
- *    unit stride -- the reference assumes it too (`+ t`, `+ 1`, `+ 2`: ...c:492-495, 556).
+ *    THTensor (size[], stride[], data).  Strides are in ELEMENTS.  The reference assumes a unit stride
+ *    on the last dimension (`+ t`, `+ 1`, `+ 2`: ...c:492-495, 556); this library honours ANY stride
+ *    there as well, so the `B x D x H x W x C` view of a contiguous `B x C x D x H x W` tensor can be
+ *    passed directly instead of through the materialised nn.Transpose copies of stn3dtorch/test.lua:17,21
+ *    and models/alignet.lua:11,14,21.
  *  - volume layout channels-last `B x D x H x W x C`; grid `B x D x H x W x G`, components
  *    (z, y, x[, dis]) in [-1, 1]; -1 -> index 0, +1 -> index size-1; zero padding outside.
  *  - volstn_b200_* take DEVICE pointers and a CUDA stream (pass the caller's current stream, as
@@ -81,6 +84,7 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_ALGO_DIRECT 0x100u /* one red.global per in-bounds corner (vector red for C = 2, 4)   */
 #define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA */
 #define VOLSTN_ALGO_QUAD 0x400u   /* backward, C = 1: x0/x0+1 contributions as one 16-byte reduction on the aligned quad */
+#define VOLSTN_ALGO_ROW 0x500u    /* the row kernels (a warp per output row; the path of strided / planar tensors) even for packed tensors */
 #define VOLSTN_ALGO_PAIR 0x300u   /* direct kernels with packed fp32x2 arithmetic (measured slower; kept for A/B) */
 /* debugging / A-B timing: force the slower but always-valid code paths (results are identical) */
 #define VOLSTN_DEBUG_NO_FAST 0x10000u   /* every warp takes the exact predicated path            */
@@ -119,6 +123,41 @@ int volstn_b200_sampler_backward(int dtype, int G, const volstn_tensor5 *vol, co
  * raster order over (b, z, y, x) of the grid.  vol_size = {B, D, H, W, C}. */
 int volstn_b200_sampler_indices(int dtype, int G, const int64_t vol_size[5], const volstn_tensor5 *grid,
                                 int32_t *idx, uint8_t *mask, void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused modules, DEVICE pointers, float only.  They are NEW
+ * entry points -- the reference has no counterpart to bind -- whose results are, bit for bit, those of
+ * the chain of un-fused calls they replace (gradients of reductions: within the stated tolerance).
+ * ------------------------------------------------------------------------------------------- */
+
+/* out = BilinearSamplerVolumetric(vol, VolumetricGridGenerator(oD, oH, oW)(T)) without the 16 B/voxel grid
+ * ever touching memory: the `projector` of stn3dtorch/test.lua:15-25 and the loader-side affine
+ * augmentation (dataset_2d.lua:285-311).  T: B x 4 x 4 (row 3 unused); out: B x oD x oH x oW x C.
+ * Replaces volstn_b200_gridgen_forward + volstn_b200_sampler_forward (G = 4). */
+int volstn_b200_affine_sampler_forward(int dtype, const void *T, const volstn_tensor5 *vol,
+                                       const volstn_tensor5 *out, unsigned flags, void *cuda_stream);
+/* gradVol (scatter-add; VOLSTN_BWD_ZERO_GRADVOL / VOLSTN_BWD_ONLY_GRID as for the sampler) and
+ * gradT = VolumetricGridGenerator:updateGradInput(BilinearSamplerVolumetric gradGrid) (assigned; row 3 is zero
+ * because gradGrid[..., 3] is, ...c:822).  Deterministic two-stage reduction; workspace as reported below. */
+int volstn_b200_affine_sampler_backward(int dtype, const void *T, const volstn_tensor5 *vol,
+                                        const volstn_tensor5 *gradVol, void *gradT, const volstn_tensor5 *gradOut,
+                                        void *workspace, size_t workspace_bytes, unsigned flags, void *cuda_stream);
+size_t volstn_b200_affine_sampler_backward_workspace(int64_t B, int64_t oD, int64_t oH, int64_t oW);
+
+/* ALIGNet's warp: the B x 3 x cD x cH x cW control cage (models/alignet_2d.lua:136, after nn.Cumsum and
+ * the +beta) is up-sampled to the resolution of `out` by sampling it at the identity field
+ * (models/alignet_2d.lua:138-147, alignet.lua:27-39 lifted to 3-D) and the source volume is sampled at the
+ * resulting field -- in one pass, the full-resolution field never exists.  Replaces
+ *   gridgen_forward(I) ; sampler_forward(cage volume B x cD x cH x cW x 4, identity field) ; sampler_forward(vol, field).
+ * cage_dims = {cD, cH, cW}, each <= 64, cW <= 20.  out: B x oD x oH x oW x C, extents >= 2. */
+int volstn_b200_cage_warp_forward(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
+                                  const volstn_tensor5 *out, unsigned flags, void *cuda_stream);
+/* gradVol as for the sampler; gradCage (B x 3 x cD x cH x cW, ASSIGNED) = the cage up-sample's gradInput[1] of the
+ * source warp's gradGrid.  VOLSTN_BWD_ONLY_GRID skips gradVol (the source is data, models/alignet_2d.lua:23-24),
+ * VOLSTN_BWD_ONLY_VOLUME skips gradCage. */
+int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
+                                   const volstn_tensor5 *gradVol, void *gradCage, const volstn_tensor5 *gradOut,
+                                   unsigned flags, void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Grid generator (nn.VolumetricGridGenerator), DEVICE pointers, contiguous tensors

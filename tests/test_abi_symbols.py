@@ -79,9 +79,24 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.volstn_b200_sampler_forward(0, 4, vol, g3, out, 0, None) == _abi.ERR_SHAPE        # lua:34
     bad_out = desc((2, 3, 3, 2, 1))
     assert lib.volstn_b200_sampler_forward(0, 4, vol, grid, bad_out, 0, None) == _abi.ERR_SHAPE  # lua:73
+    # the HOST entry points take contiguous tensors only (the device ones honour any strides)
     strided = desc((2, 3, 3, 3, 4))
     strided.stride[4] = 2
-    assert lib.volstn_b200_sampler_forward(0, 4, vol, strided, out, 0, None) == _abi.ERR_LAYOUT
+    assert lib.volstn_b200_host_sampler_forward(ctypes.c_void_p(1), 0, 4, vol, strided, out, 0) == _abi.ERR_LAYOUT
+    # fused modules: float only, generator extents > 1, bounded cage, exclusive ONLY_ flags
+    o5 = desc((2, 3, 3, 3, 1))
+    assert lib.volstn_b200_affine_sampler_forward(1, 1 << 20, vol, o5, 0, None) == _abi.ERR_UNSUPPORTED
+    assert lib.volstn_b200_affine_sampler_forward(0, 1 << 20, vol, desc((2, 1, 3, 3, 1)), 0, None) == _abi.ERR_SHAPE
+    assert lib.volstn_b200_affine_sampler_forward(0, 1 << 20, vol, desc((3, 3, 3, 3, 1)), 0, None) == _abi.ERR_SHAPE
+    assert lib.volstn_b200_affine_sampler_backward(0, 1 << 20, vol, vol, 1 << 20, o5, 1 << 20, 8, 0, None) == _abi.ERR_WORKSPACE
+    assert lib.volstn_b200_affine_sampler_backward(0, 1 << 20, vol, vol, 1 << 20, o5, 1 << 20, 1 << 30, 3, None) == _abi.ERR_ARG
+    assert lib.volstn_b200_affine_sampler_backward_workspace(4, 8, 8, 8) > 0
+    cd = (ctypes.c_int64 * 3)(8, 8, 32)
+    assert lib.volstn_b200_cage_warp_forward(0, 1 << 20, cd, vol, o5, 0, None) == _abi.ERR_UNSUPPORTED
+    cd = (ctypes.c_int64 * 3)(8, 0, 8)
+    assert lib.volstn_b200_cage_warp_forward(0, 1 << 20, cd, vol, o5, 0, None) == _abi.ERR_SHAPE
+    cd = (ctypes.c_int64 * 3)(8, 8, 8)
+    assert lib.volstn_b200_cage_warp_backward(0, 1 << 20, cd, vol, vol, 1 << 20, o5, 3, None) == _abi.ERR_ARG
     # empty batch: nothing to do, no launch, ok
     e_vol, e_grid, e_out = desc((0, 4, 4, 4, 1)), desc((0, 3, 3, 3, 4)), desc((0, 3, 3, 3, 1))
     n0 = lib.volstn_b200_launch_count()

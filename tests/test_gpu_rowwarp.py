@@ -1,0 +1,289 @@
+"""Parity of the ROW kernels (alignet_b200/csrc/rowwarp.cu) -- SURVEY.md section 8, rows f1, f2, f3.
+
+Every case is checked against the ORACLE CHAIN of the un-fused reference modules on the same inputs:
+
+  f2  strided / planar tensors   oracle.sampler_* on contiguous copies of the permuted views
+  f3  AffineSamplerVolumetric    grid generator -> oracle.sampler_*            (stn3dtorch/test.lua:15-25)
+  f1  CageWarpVolumetric         identity base grid -> oracle.sampler_forward(cage volume) -> oracle.sampler_*(source)
+                                 (models/alignet_2d.lua:136-147, alignet.lua:4-39 lifted to 3-D)
+
+Tolerances (per tensor): out, gradGrid and the floor/mask decisions behind them bit-exact; gradVol and gradCage
+(atomic accumulation order) max|d| <= 1e-4 * max|ref|; gradT (a reduction over all voxels) <= 1e-5 * max|ref|.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from alignet_b200 import _abi, synth
+from alignet_b200 import nn as vnn
+from oracle import oracle
+from tests._util import bits_equal, describe_mismatch, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().contiguous().cpu().numpy()
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# the row kernels on the packed layout (forced with VOLSTN_ALGO_ROW): same contract as the packed kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G", [4, 3])
+@pytest.mark.parametrize("C", [1, 2, 3, 6])
+@pytest.mark.parametrize("oshape", [(7, 10, 37), (5, 9, 20), (3, 5, 70)])
+def test_row_kernels_on_packed_tensors(G, C, oshape):
+    for gk in ("g1", "g2", "g3", "g4", "g5"):
+        rng = np.random.default_rng(100 * G + 10 * C + ord(gk[1]) + oshape[2])
+        B, ishape = 3, (9, 11, 13)
+        vol = synth.volume("v1", B, *ishape, C, rng)
+        grid = synth.grid(gk, B, *oshape, rng, G=G, csz=4)
+        go = synth.grad_output(B, *oshape, C, rng)
+        ref_out = oracle.sampler_forward(vol, grid, G)
+        ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go, G)
+        m = vnn.BilinearSamplerVolumetric(gridWidth=G, algo=_abi.ALGO_ROW)
+        out = host(m.updateOutput([dev(vol), dev(grid)]))
+        assert bits_equal(out, ref_out), (gk, describe_mismatch(out, ref_out))
+        gv, gg = m.updateGradInput([dev(vol), dev(grid)], dev(go))
+        assert bits_equal(host(gg), ref_gg), (gk, describe_mismatch(host(gg), ref_gg))
+        assert max_rel(host(gv), ref_gv) <= 1e-4, gk
+        for kw in (dict(onlyGrid=True), dict(onlyVolume=True)):
+            m2 = vnn.BilinearSamplerVolumetric(gridWidth=G, algo=_abi.ALGO_ROW, **kw)
+            gv2, gg2 = m2.updateGradInput([dev(vol), dev(grid)], dev(go))
+            if "onlyGrid" in kw:
+                assert bits_equal(host(gg2), ref_gg) and float(gv2.abs().max()) == 0.0
+            else:
+                assert max_rel(host(gv2), ref_gv) <= 1e-4 and float(gg2.abs().max()) == 0.0
+
+
+def test_row_kernels_special_values(golden):
+    """non-finite and huge coordinates, exact +-1: the golden vectors of the reference's C code"""
+    for (name, G, dt), c in golden.items():
+        if dt != "float32":
+            continue
+        m = vnn.BilinearSamplerVolumetric(gridWidth=G, algo=_abi.ALGO_ROW)
+        out = host(m.updateOutput([dev(c["vol"]), dev(c["grid"])]))
+        assert bits_equal(out, c["out"]), (name, G, describe_mismatch(out, c["out"]))
+        gv, gg = m.updateGradInput([dev(c["vol"]), dev(c["grid"])], dev(c["gradOut"]))
+        assert bits_equal(host(gg), c["gradGrid"]), (name, G)
+        assert np.array_equal(np.isnan(host(gv)), np.isnan(c["gradVol"])) and max_rel(host(gv), c["gradVol"]) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# f2: channel-first tensors in place (no nn.Transpose copies)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G", [4, 3])
+@pytest.mark.parametrize("C", [1, 2, 4])
+def test_channel_first_layout(G, C):
+    rng = np.random.default_rng(31 + G + C)
+    B, ishape, oshape = 2, (6, 9, 12), (5, 8, 41)
+    vol = synth.volume("v1", B, *ishape, C, rng)            # B D H W C
+    for gk in ("g2", "g4"):
+        grid = synth.grid(gk, B, *oshape, rng, G=G, csz=4)
+        go = synth.grad_output(B, *oshape, C, rng)
+        ref_out = oracle.sampler_forward(vol, grid, G)
+        ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go, G)
+        cf = lambda a: dev(np.moveaxis(a, -1, 1))           # materialise B C D H W
+        m = vnn.BilinearSamplerVolumetric(gridWidth=G, layout="BCDHW")
+        out = m.updateOutput([cf(vol), cf(grid)])
+        assert tuple(out.shape) == (B, C) + oshape and out.is_contiguous()
+        assert bits_equal(host(out.permute(0, 2, 3, 4, 1)), ref_out), describe_mismatch(host(out.permute(0, 2, 3, 4, 1)), ref_out)
+        gv, gg = m.updateGradInput([cf(vol), cf(grid)], cf(go))
+        assert tuple(gv.shape) == (B, C) + ishape and tuple(gg.shape) == (B, G) + oshape
+        assert bits_equal(host(gg.permute(0, 2, 3, 4, 1)), ref_gg)
+        assert max_rel(host(gv.permute(0, 2, 3, 4, 1)), ref_gv) <= 1e-4
+
+
+def test_projector_permutation_direct_abi():
+    """stn3dtorch/test.lua:17,21: nn.Transpose({2,4},{4,5}) turns B x C x D x H x W into B x H x D x W x C, and
+    nn.Transpose({4,5},{2,4}) undoes it on the output.  Here both are views handed to the C ABI."""
+    rng = np.random.default_rng(41)
+    B, C, D, H, W = 2, 2, 6, 7, 9
+    vol_cf = rng.standard_normal((B, C, D, H, W)).astype(np.float32)
+    view = lambda t: t.permute(0, 3, 2, 4, 1)               # B H D W C
+    grid = synth.grid("g5", B, H, D, W, rng)
+    go_cf = rng.standard_normal((B, C, D, H, W)).astype(np.float32)
+    tv, tg, tgo = dev(vol_cf), dev(grid), dev(go_cf)
+    out_cf = torch.empty((B, C, D, H, W), device="cuda")
+    gv_cf = torch.empty_like(tv)
+    gg = torch.empty_like(tg)
+    lib, d = _abi.lib(), vnn._desc
+    _abi.check(lib.volstn_b200_sampler_forward(0, 4, d(view(tv)), d(tg), d(view(out_cf)), 0, stream()), "fwd")
+    _abi.check(lib.volstn_b200_sampler_backward(0, 4, d(view(tv)), d(tg), d(view(gv_cf)), d(gg), d(view(tgo)),
+                                                _abi.BWD_ZERO_GRADVOL, stream()), "bwd")
+    torch.cuda.synchronize()
+    pv = lambda a: np.ascontiguousarray(np.transpose(a, (0, 3, 2, 4, 1)))
+    ref_out = oracle.sampler_forward(pv(vol_cf), grid)
+    ref_gv, ref_gg = oracle.sampler_backward(pv(vol_cf), grid, pv(go_cf))
+    assert bits_equal(host(view(out_cf)), ref_out)
+    assert bits_equal(host(gg), ref_gg)
+    assert max_rel(host(view(gv_cf)), ref_gv) <= 1e-4
+
+
+def test_channel_first_double_uses_generic_kernels():
+    rng = np.random.default_rng(43)
+    B, C = 2, 3
+    vol = synth.volume("v1", B, 5, 6, 7, C, rng, np.float64)
+    grid = synth.grid("g4", B, 4, 5, 9, rng, np.float64)
+    go = synth.grad_output(B, 4, 5, 9, C, rng, np.float64)
+    cf = lambda a: dev(np.moveaxis(a, -1, 1))
+    m = vnn.BilinearSamplerVolumetric(layout="BCDHW")
+    out = m.updateOutput([cf(vol), cf(grid)])
+    assert bits_equal(host(out.permute(0, 2, 3, 4, 1)), oracle.sampler_forward(vol, grid))
+    gv, gg = m.updateGradInput([cf(vol), cf(grid)], cf(go))
+    ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go)
+    assert bits_equal(host(gg.permute(0, 2, 3, 4, 1)), ref_gg)
+    assert max_rel(host(gv.permute(0, 2, 3, 4, 1)), ref_gv) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# f3: grid generator folded into the sampler
+# ---------------------------------------------------------------------------------------------
+def random_affine(B, rng, scale=0.3):
+    T = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    q, _ = np.linalg.qr(rng.standard_normal((B, 3, 3)))
+    T[:, :3, :3] = q.astype(np.float32)
+    T[:, :3, 3] = (scale * rng.standard_normal((B, 3))).astype(np.float32)
+    T[0] = np.eye(4, dtype=np.float32)                      # the identity: every coordinate exactly on the lattice
+    return T
+
+
+@pytest.mark.parametrize("C", [1, 3])
+@pytest.mark.parametrize("oshape", [(6, 9, 40), (5, 7, 16), (64, 2, 3)])
+def test_affine_sampler_matches_generator_then_sampler(C, oshape):
+    rng = np.random.default_rng(51 + C + oshape[2])
+    B, ishape = 3, (8, 9, 11)
+    vol = synth.volume("v1", B, *ishape, C, rng)
+    T = random_affine(B, rng)
+    go = synth.grad_output(B, *oshape, C, rng)
+    gen = vnn.VolumetricGridGenerator(*oshape)
+    grid = host(gen.updateOutput(dev(T)))                   # the un-fused first stage (parity-tested on its own)
+    assert np.abs(grid - oracle.gridgen_forward(T, *oshape)).max() <= 1e-6
+    ref_out = oracle.sampler_forward(vol, grid)
+    ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go)
+    ref_gT = oracle.gridgen_backward(ref_gg)
+    m = vnn.AffineSamplerVolumetric(*oshape)
+    out = host(m.updateOutput([dev(vol), dev(T)]))
+    assert bits_equal(out, ref_out), describe_mismatch(out, ref_out)
+    gv, gT = m.updateGradInput([dev(vol), dev(T)], dev(go))
+    assert max_rel(host(gv), ref_gv) <= 1e-4
+    assert max_rel(host(gT), ref_gT) <= 1e-5, (host(gT)[1], ref_gT[1])
+    assert float(gT[:, 3].abs().max()) == 0.0               # gradGrid[..., 3] = 0 (...c:822)
+    # channel-first volume in place, as in the projector
+    m2 = vnn.AffineSamplerVolumetric(*oshape, layout="BCDHW")
+    out2 = m2.updateOutput([dev(np.moveaxis(vol, -1, 1)), dev(T)])
+    assert bits_equal(host(out2.permute(0, 2, 3, 4, 1)), ref_out)
+    gv2, gT2 = m2.updateGradInput([dev(np.moveaxis(vol, -1, 1)), dev(T)], dev(np.moveaxis(go, -1, 1)))
+    assert max_rel(host(gv2.permute(0, 2, 3, 4, 1)), ref_gv) <= 1e-4 and max_rel(host(gT2), ref_gT) <= 1e-5
+
+
+def test_affine_sampler_projector_of_the_reference_test():
+    """stn3dtorch/test.lua:87: the 90 degree rotation permutes and flips axes of the volume exactly"""
+    N = 16
+    rng = np.random.default_rng(7)
+    vol = (rng.standard_normal((1, N, N, N, 1)) >= 0.5).astype(np.float32)      # test.lua:83
+    T = np.zeros((1, 4, 4), np.float32)
+    T[0, 0, 0] = 1
+    T[0, 1, 2] = 1
+    T[0, 2, 1] = -1
+    T[0, 3, 3] = 1
+    out = host(vnn.AffineSamplerVolumetric(N, N, N).updateOutput([dev(vol), dev(T)]))
+    grid = host(vnn.VolumetricGridGenerator(N, N, N).updateOutput(dev(T)))
+    assert bits_equal(out, oracle.sampler_forward(vol, grid))
+    # out[z, y, x] = vol[z, x, N-1-y] up to the rounding of the lattice coordinates
+    expect = np.flip(np.swapaxes(vol, 2, 3), axis=2)
+    assert np.abs(out - expect).max() <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# f1: cage up-sample + source warp
+# ---------------------------------------------------------------------------------------------
+def cage_chain_oracle(src, cage, oshape, go=None):
+    """the un-fused module chain on the CPU oracle"""
+    B = src.shape[0]
+    base = oracle.gridgen_base(*oshape)                                        # fieldI (identity through the generator)
+    field_i = np.ascontiguousarray(np.broadcast_to(base, (B,) + base.shape))
+    cage_vol = np.ones(cage.shape[:1] + cage.shape[2:] + (4,), np.float32)     # channels-last, 4th component constant
+    cage_vol[..., :3] = np.moveaxis(cage, 1, -1)
+    field = oracle.sampler_forward(cage_vol, field_i)
+    out = oracle.sampler_forward(src, field)
+    if go is None:
+        return out
+    gsrc, gfield = oracle.sampler_backward(src, field, go)
+    gcage_vol, _ = oracle.sampler_backward(cage_vol, field_i, gfield)
+    return out, gsrc, np.ascontiguousarray(np.moveaxis(gcage_vol[..., :3], -1, 1))
+
+
+@pytest.mark.parametrize("cdims", [(4, 4, 4), (8, 8, 8), (3, 5, 2), (12, 12, 12)])
+@pytest.mark.parametrize("oshape", [(16, 16, 16), (7, 10, 37), (9, 6, 70)])
+@pytest.mark.parametrize("C", [1, 2])
+def test_cage_warp_matches_module_chain(cdims, oshape, C):
+    rng = np.random.default_rng(61 + cdims[0] + oshape[2] + C)
+    B = 3
+    src = synth.volume("v1", B, *oshape, C, rng)
+    cage = np.stack([synth.alignet_cage(1, max(cdims), rng)[0][:, :cdims[0], :cdims[1], :cdims[2]] for _ in range(B)]).astype(np.float32)
+    cage[1] = rng.uniform(-1.6, 1.6, cage[1].shape).astype(np.float32)          # folded, partly outside the volume
+    go = synth.grad_output(B, *oshape, C, rng)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    m = vnn.CageWarpVolumetric()
+    out = host(m.updateOutput([dev(src), dev(cage)]))
+    assert bits_equal(out, ref_out), describe_mismatch(out, ref_out)
+    gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+    assert max_rel(host(gsrc), ref_gsrc) <= 1e-4
+    assert max_rel(host(gcage), ref_gcage) <= 1e-4, describe_mismatch(host(gcage), ref_gcage)
+    m2 = vnn.CageWarpVolumetric(onlyGrid=True)
+    gsrc2, gcage2 = m2.updateGradInput([dev(src), dev(cage)], dev(go))
+    assert float(gsrc2.abs().max()) == 0.0 and max_rel(host(gcage2), ref_gcage) <= 1e-4
+
+
+def test_cage_warp_identity_cage_reproduces_the_source():
+    """ALIGNet at initialisation (weight 0, bias del: models/alignet_2d.lua:77-80,118-119): the cage is
+    linspace(-1, 1, csz) per axis and the warp is the identity."""
+    N, csz, B = 32, 8, 2
+    rng = np.random.default_rng(3)
+    src = synth.volume("v2", B, N, N, N, 1, rng)
+    ax = np.linspace(-1, 1, csz).astype(np.float32)
+    cage = np.empty((B, 3, csz, csz, csz), np.float32)
+    cage[:, 0] = ax[:, None, None]
+    cage[:, 1] = ax[None, :, None]
+    cage[:, 2] = ax[None, None, :]
+    out = host(vnn.CageWarpVolumetric().updateOutput([dev(src), dev(cage)]))
+    assert bits_equal(out, cage_chain_oracle(src, cage, (N, N, N)))
+    assert np.abs(out - src).max() <= 2e-5
+
+
+def test_cage_warp_output_resolution_differs_from_source():
+    rng = np.random.default_rng(5)
+    src = synth.volume("v1", 2, 6, 7, 8, 1, rng)
+    cage = synth.alignet_cage(2, 4, rng).astype(np.float32)
+    oshape = (5, 9, 33)
+    go = synth.grad_output(2, *oshape, 1, rng)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    m = vnn.CageWarpVolumetric(*oshape)
+    assert bits_equal(host(m.updateOutput([dev(src), dev(cage)])), ref_out)
+    gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+    assert max_rel(host(gsrc), ref_gsrc) <= 1e-4 and max_rel(host(gcage), ref_gcage) <= 1e-4
+
+
+def test_fused_modules_reject_what_they_do_not_support():
+    lib, d = _abi.lib(), vnn._desc
+    v = torch.zeros((1, 4, 4, 4, 1), device="cuda", dtype=torch.float64)
+    o = torch.zeros((1, 4, 4, 4, 1), device="cuda", dtype=torch.float64)
+    T = torch.eye(4, device="cuda", dtype=torch.float64).view(1, 4, 4)
+    assert lib.volstn_b200_affine_sampler_forward(_abi.F64, T.data_ptr(), d(v), d(o), 0, stream()) == _abi.ERR_UNSUPPORTED
+    vf, of = v.float(), o.float()
+    dims = (ctypes.c_int64 * 3)(4, 4, 32)
+    cage = torch.zeros((1, 3, 4, 4, 32), device="cuda")
+    assert lib.volstn_b200_cage_warp_forward(_abi.F32, cage.data_ptr(), dims, d(vf), d(of), 0, stream()) == _abi.ERR_UNSUPPORTED
+    o1 = torch.zeros((1, 1, 4, 4, 1), device="cuda")      # extent 1: the generator asserts depth > 1 (lua:6-8)
+    assert lib.volstn_b200_affine_sampler_forward(_abi.F32, T.float().data_ptr(), d(vf), d(o1), 0, stream()) == _abi.ERR_SHAPE
