@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libvolstn_b200.so")
+LIB_PATH = os.environ.get("VOLSTN_B200_LIB") or os.path.join(HERE, "csrc", "libvolstn_b200.so")
 
 # status codes / enums / flags (mirror include/volstn_b200.h)
 OK, ERR_ARG, ERR_SHAPE, ERR_LAYOUT, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_WORKSPACE = range(8)

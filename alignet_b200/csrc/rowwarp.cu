@@ -12,6 +12,7 @@
 // `out` and gradGrid have the bits of the reference CPU code; the AFFINE / CAGE coordinates are computed with the
 // operation order of k_gridgen_fwd and of the sampler itself, so a fused call has the bits of the un-fused
 // module chain (tests/test_gpu_rowwarp.py).
+#include <cstdlib>
 #include <cstring>
 
 #include "rowwarp.cuh"
@@ -41,7 +42,9 @@ struct RowSmem {
 };
 
 __host__ __device__ inline int row_cells(const RowArgs &a) { return (a.cD + 1) * (a.cH + 1) * (a.cW + 1); }
-__host__ __device__ inline int row_owp(const RowArgs &a) { return (a.s.oW + 31) & ~31; }
+// staging row length: a multiple of 32 plus 8, so that the three channels of a cage cell (rows c and 3 + c of the
+// stage) fall into different shared-memory banks when the item lanes sum their segments
+__host__ __device__ inline int row_owp(const RowArgs &a) { return ((a.s.oW + 31) & ~31) + 8; }
 
 template <int SRC, bool BWD>
 __host__ __device__ inline size_t row_smem_bytes(const RowArgs &a, bool two_rows) {
@@ -278,22 +281,40 @@ struct RowSlot {
   bool valid;
 };
 
+// (z, y) of the warp's current row is carried along (one divide per warp, not per row)
 template <bool TWO_ROWS>
-__device__ __forceinline__ void row_slots(RowSlot (&sl)[2], int r, int r_end, int xb, int lane, int oH, int oW) {
+__device__ __forceinline__ void row_slots(RowSlot (&sl)[2], int r, int r_end, int z, int y, int xb, int lane, int oH,
+                                          int oW) {
 #pragma unroll
   for (int v = 0; v < 2; v++) {
-    const int rr = TWO_ROWS ? r + v : r;
-    const int rc = min(rr, r_end - 1);
-    sl[v].z = rc / oH;
-    sl[v].y = rc - sl[v].z * oH;
+    const bool second = TWO_ROWS && v == 1 && r + 1 < r_end;  // the second row of the trip (clamped to the first at the end)
+    const bool wrap = second && y + 1 == oH;
+    sl[v].z = wrap ? z + 1 : z;
+    sl[v].y = second ? (wrap ? 0 : y + 1) : y;
     const int x = xb + lane + (TWO_ROWS ? 0 : 32 * v);
-    sl[v].valid = rr < r_end && x < oW;
+    sl[v].valid = (!TWO_ROWS || v == 0 || r + 1 < r_end) && x < oW;
     sl[v].x = min(x, oW - 1);
   }
 }
+__device__ __forceinline__ void row_advance(int &z, int &y, int step, int oH) {
+  y += step;
+  if (y >= oH) y -= oH, z++;  // step <= 2 <= oH
+}
+
+// Resident CTAs per SM the kernels are compiled for (a register cap of 48 / 64).  Measured on a B200 with every
+// value from 1 to 6 (profiles/r02_fbench_history.txt): without a cap ptxas takes 56-128 registers and occupancy
+// falls to 24-45 %; caps of 5-6 spill in the backward kernels and lose more than the occupancy gains.
+#ifndef ROW_MIN_CTAS
+#define ROW_MIN_CTAS 0
+#endif
+constexpr int row_min_ctas(int src, bool bwd, bool c1) {
+  if (ROW_MIN_CTAS) return ROW_MIN_CTAS;
+  if (!c1) return 3;
+  return (src == ROW_SRC_GRID && !bwd) ? 5 : 4;
+}
 
 template <int SRC, bool AOS4, bool C1, bool TWO_ROWS>
-__global__ void __launch_bounds__(kRowThreads) k_row_fwd(const RowArgs a) {
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_row_fwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SamplerArgs<float> &s = a.s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -309,10 +330,11 @@ __global__ void __launch_bounds__(kRowThreads) k_row_fwd(const RowArgs a) {
   const int sW = C1 ? 1 : a.vW;
   int r = (blockIdx.x * kRowWarps + wid) * a.rows_per_warp;
   const int r_end = min(r + a.rows_per_warp, s.oD * s.oH);
-  for (; r < r_end; r += TWO_ROWS ? 2 : 1) {
+  int z = r / s.oH, y = r - z * s.oH;
+  for (; r < r_end; r += TWO_ROWS ? 2 : 1, row_advance(z, y, TWO_ROWS ? 2 : 1, s.oH)) {
     for (int xb = 0; xb < s.oW; xb += TWO_ROWS ? 32 : 64) {
       RowSlot sl[2];
-      row_slots<TWO_ROWS>(sl, r, r_end, xb, lane, s.oH, s.oW);
+      row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
       VoxelSetup<float> su[2];
       int tier = 2;
 #pragma unroll
@@ -403,7 +425,7 @@ struct CageAcc {
 };
 
 template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV>
-__global__ void __launch_bounds__(kRowThreads) k_row_bwd(const RowArgs a) {
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];
   const SamplerArgs<float> &s = a.s;
@@ -432,10 +454,11 @@ __global__ void __launch_bounds__(kRowThreads) k_row_bwd(const RowArgs a) {
 
   int r = (blockIdx.x * kRowWarps + wid) * a.rows_per_warp;
   const int r_end = min(r + a.rows_per_warp, s.oD * s.oH);
-  for (; r < r_end; r += TWO_ROWS ? 2 : 1) {
+  int z = r / s.oH, y = r - z * s.oH;
+  for (; r < r_end; r += TWO_ROWS ? 2 : 1, row_advance(z, y, TWO_ROWS ? 2 : 1, s.oH)) {
     for (int xb = 0; xb < s.oW; xb += TWO_ROWS ? 32 : 64) {
       RowSlot sl[2];
-      row_slots<TWO_ROWS>(sl, r, r_end, xb, lane, s.oH, s.oW);
+      row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
       VoxelSetup<float> su[2];
       int tier = 2;
 #pragma unroll
@@ -510,10 +533,9 @@ __global__ void __launch_bounds__(kRowThreads) k_row_bwd(const RowArgs a) {
       __syncwarp();
 #pragma unroll
       for (int v = 0; v < (TWO_ROWS ? 2 : 1); v++) {
-        const int rr = r + v;
-        if (rr < r_end) {
-          const int z = rr / s.oH, y = rr - z * s.oH;
-          cacc.row(m, a, st + v * 6 * owp, owp, z, y, lane);
+        if (r + v < r_end) {
+          const bool wrap = v == 1 && y + 1 == s.oH;
+          cacc.row(m, a, st + v * 6 * owp, owp, wrap ? z + 1 : z, v == 1 ? (wrap ? 0 : y + 1) : y, lane);
         }
       }
       __syncwarp();
@@ -646,13 +668,20 @@ int bwd_mode(const RowArgs &a, const RowPlan &p, int B, bool og, bool ov, cudaSt
 }  // namespace
 
 void row_geometry(int64_t B, int64_t rows, int src, int two_rows, int *nblk, int *rows_per_warp) {
-  // ~4 waves of 148 SMs x 8 resident CTAs over the whole batch; the cage source has a heavier prologue
-  // (cage + axis tables into shared memory), so its CTAs are made four times longer
+  // ~4 waves of 148 SMs x 8 resident CTAs over the whole batch, but at least 4 rows per warp; the cage source has
+  // a heavier prologue / epilogue (cage, axis tables and the cage gradient in shared memory), so its CTAs are twice
+  // as long and never shorter than 8 rows per warp.  Swept on a B200 at 32^3 x 32 and 64^3 x 64
+  // (profiles/r02_fbench_history.txt): flat between 4 and 14 rows, -15 % at 28, -30 % at 56.
   int64_t want = (int64_t)kSMs * 8 * 4 / (B > 0 ? B : 1);
-  if (src == ROW_SRC_CAGE) want /= 4;
+  if (src == ROW_SRC_CAGE) want /= 2;
   if (want < 1) want = 1;
   int64_t rpw = (rows + want * kRowWarps - 1) / (want * kRowWarps);
-  if (rpw < 2) rpw = 2;
+  const int64_t floor_rows = src == ROW_SRC_CAGE ? 8 : 4;
+  if (rpw < floor_rows) rpw = floor_rows;
+  if (const char *e = getenv("VOLSTN_ROW_RPW")) {  // tuning only
+    const long long v = atoll(e);
+    if (v > 0) rpw = v;
+  }
   if (two_rows) rpw = (rpw + 1) & ~(int64_t)1;
   int64_t blocks = (rows + rpw * kRowWarps - 1) / (rpw * kRowWarps);
   if (blocks < 1) blocks = 1;
