@@ -65,6 +65,10 @@ SIGNATURES = {
     "volstn_b200_host_sampler_backward": (_i, [_vp, _i, _i, _P5, _P5, _P5, _P5, _P5, _u]),
     "volstn_b200_host_gridgen_forward": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i64, _i64]),
     "volstn_b200_host_gridgen_backward": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i64, _i64]),
+    "volstn_b200_host_affine_sampler_forward": (_i, [_vp, _i, _vp, _P5, _P5, _u]),
+    "volstn_b200_host_affine_sampler_backward": (_i, [_vp, _i, _vp, _P5, _P5, _vp, _P5, _u]),
+    "volstn_b200_host_cage_warp_forward": (_i, [_vp, _i, _vp, _pi64, _P5, _P5, _u]),
+    "volstn_b200_host_cage_warp_backward": (_i, [_vp, _i, _vp, _pi64, _P5, _P5, _vp, _P5, _u]),
     "volstn_b200_host_cumsum_forward": (_i, [_vp, _i, _vp, _vp, _i64, _i, _pi64]),
     "volstn_b200_host_cumsum_backward": (_i, [_vp, _i, _vp, _vp, _i64, _i, _pi64]),
     "volstn_b200_abi_version": (_i, []),

@@ -117,6 +117,81 @@ int ensure_keep(volstn_host_ctx *c, void **buf, size_t *cap, size_t bytes) {
 
 size_t sample_elems(const volstn_tensor5 *t) { return (size_t)(t->size[1] * t->size[2] * t->size[3] * t->size[4]); }
 
+// ---------------------------------------------------------------------------------------------
+// generic batch-sliced staging for the fused modules: every tensor is contiguous with the batch outermost
+// ---------------------------------------------------------------------------------------------
+struct HostSpan {
+  const void *src;  // host pointer (inputs) ...
+  void *dst;        // ... or host pointer (outputs)
+  size_t per;       // bytes per sample
+  bool zero;        // outputs only: zero-fill the device slice before the launch
+};
+
+template <typename Launch>
+int run_sliced(volstn_host_ctx *c, int64_t B, const HostSpan *in, int nin, const HostSpan *out, int nout, size_t scratch_per,
+               Launch launch) {
+  size_t per = scratch_per;
+  for (int i = 0; i < nin; i++) per += in[i].per;
+  for (int i = 0; i < nout; i++) per += out[i].per;
+  const int64_t bs = slice_batch(B, per);
+  size_t need = align_up(scratch_per * bs);
+  for (int i = 0; i < nin; i++) need += align_up(in[i].per * bs);
+  for (int i = 0; i < nout; i++) need += align_up(out[i].per * bs);
+  int rc = VOLSTN_OK;
+  int slice = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
+    const int64_t nb = std::min(bs, B - b0);
+    const int s = slice % volstn_host_ctx::kSlots;
+    if ((rc = ensure_arena(c, s, need))) break;
+    cudaStream_t st = c->stream[s];
+    char *p = static_cast<char *>(c->arena[s]);
+    void *din[8], *dout[8];
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nin && e == cudaSuccess; i++) {
+      din[i] = p;
+      p += align_up(in[i].per * bs);
+      e = cudaMemcpyAsync(din[i], static_cast<const char *>(in[i].src) + b0 * in[i].per, nb * in[i].per,
+                          cudaMemcpyHostToDevice, st);
+    }
+    for (int i = 0; i < nout && e == cudaSuccess; i++) {
+      dout[i] = p;
+      p += align_up(out[i].per * bs);
+      if (out[i].zero && out[i].per) e = cudaMemsetAsync(dout[i], 0, nb * out[i].per, st);
+    }
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+    if ((rc = launch(nb, din, dout, static_cast<void *>(p), scratch_per * bs, st))) break;
+    for (int i = 0; i < nout && e == cudaSuccess; i++)
+      if (out[i].per)
+        e = cudaMemcpyAsync(static_cast<char *>(out[i].dst) + b0 * out[i].per, dout[i], nb * out[i].per,
+                            cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e);
+      break;
+    }
+  }
+  const int rs = sync_all(c);
+  return rc ? rc : rs;
+}
+
+volstn_tensor5 rehome(const volstn_tensor5 *t, int64_t nb, void *dev) {
+  volstn_tensor5 d = *t;
+  d.data = dev;
+  d.size[0] = nb;
+  return d;
+}
+
+int check_host_fused(volstn_host_ctx *c, int dtype, const volstn_tensor5 *vol, const volstn_tensor5 *outlike) {
+  if (!c || !vol || !outlike) return VOLSTN_ERR_ARG;
+  if (dtype == VOLSTN_F64) return VOLSTN_ERR_UNSUPPORTED;
+  if (dtype != VOLSTN_F32) return VOLSTN_ERR_ARG;
+  if (!desc_contiguous(vol) || !desc_contiguous(outlike)) return VOLSTN_ERR_LAYOUT;
+  if (outlike->size[0] != vol->size[0] || outlike->size[4] != vol->size[4]) return VOLSTN_ERR_SHAPE;
+  return VOLSTN_OK;
+}
+
 }  // namespace
 }  // namespace volstn
 
@@ -409,6 +484,112 @@ int volstn_b200_host_gridgen_backward(volstn_host_ctx *c, int dtype, const void 
   }
   const int rs = sync_all(c);
   return rc ? rc : rs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused modules, HOST tensors (contiguous).  The loader-side affine augmentation of the reference runs on CPU
+// tensors in the data threads (dataset_2d.lua:285-311): the fused call moves volume + T up and the warped volume
+// down -- the 16 B/voxel grid never crosses PCIe.
+// ---------------------------------------------------------------------------------------------
+int volstn_b200_host_affine_sampler_forward(volstn_host_ctx *c, int dtype, const void *T, const volstn_tensor5 *vol,
+                                            const volstn_tensor5 *out, unsigned flags) {
+  int rc = check_host_fused(c, dtype, vol, out);
+  if (rc) return rc;
+  const int64_t B = vol->size[0];
+  if (B == 0 || desc_numel(out) == 0) return volstn_b200_affine_sampler_forward(dtype, T, vol, out, flags, nullptr);
+  if (!T || !vol->data || !out->data) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const HostSpan in[2] = {{vol->data, nullptr, sample_elems(vol) * 4, false}, {T, nullptr, 64, false}};
+  const HostSpan outs[1] = {{nullptr, out->data, sample_elems(out) * 4, false}};
+  return run_sliced(c, B, in, 2, outs, 1, 0, [&](int64_t nb, void **din, void **dout, void *, size_t, cudaStream_t st) {
+    volstn_tensor5 tv = rehome(vol, nb, din[0]), to = rehome(out, nb, dout[0]);
+    return volstn_b200_affine_sampler_forward(dtype, din[1], &tv, &to, flags, st);
+  });
+}
+
+int volstn_b200_host_affine_sampler_backward(volstn_host_ctx *c, int dtype, const void *T, const volstn_tensor5 *vol,
+                                             const volstn_tensor5 *gradVol, void *gradT, const volstn_tensor5 *gradOut,
+                                             unsigned flags) {
+  int rc = check_host_fused(c, dtype, vol, gradOut);
+  if (rc) return rc;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID, ov = flags & VOLSTN_BWD_ONLY_VOLUME;
+  if ((og && ov) || (!og && !gradVol) || (!ov && !gradT)) return VOLSTN_ERR_ARG;
+  if (!og && (!desc_contiguous(gradVol) || gradVol->size[0] != vol->size[0])) return VOLSTN_ERR_LAYOUT;
+  const int64_t B = vol->size[0];
+  if (B == 0) return VOLSTN_OK;
+  if (desc_numel(gradOut) == 0) return VOLSTN_ERR_SHAPE;
+  if (!T || !vol->data || !gradOut->data) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  // gradVol is zero-filled on the device (the module's :zero(), BilinearSamplerVolumetric.lua:103); accumulate
+  // semantics are available through the device entry point only
+  const HostSpan in[3] = {{vol->data, nullptr, sample_elems(vol) * 4, false}, {T, nullptr, 64, false},
+                          {gradOut->data, nullptr, sample_elems(gradOut) * 4, false}};
+  const HostSpan outs[2] = {{nullptr, og ? nullptr : gradVol->data, og ? 0 : sample_elems(vol) * 4, true},
+                            {nullptr, gradT, ov ? (size_t)0 : (size_t)64, false}};
+  const int64_t oD = gradOut->size[1], oH = gradOut->size[2], oW = gradOut->size[3];
+  // the workspace of a slice is bounded by the one of a single-sample launch (CTAs per sample shrink as B grows)
+  const size_t ws_per = volstn_b200_affine_sampler_backward_workspace(1, oD, oH, oW);
+  return run_sliced(c, B, in, 3, outs, 2, ws_per,
+                    [&](int64_t nb, void **din, void **dout, void *ws, size_t ws_bytes, cudaStream_t st) {
+                      volstn_tensor5 tv = rehome(vol, nb, din[0]), tgo = rehome(gradOut, nb, din[2]), tgv;
+                      if (!og) tgv = rehome(gradVol, nb, dout[0]);
+                      return volstn_b200_affine_sampler_backward(dtype, din[1], &tv, og ? nullptr : &tgv, dout[1], &tgo, ws,
+                                                                 ws_bytes, flags & ~VOLSTN_BWD_ZERO_GRADVOL, st);
+                    });
+}
+
+int volstn_b200_host_cage_warp_forward(volstn_host_ctx *c, int dtype, const void *cage, const int64_t cage_dims[3],
+                                       const volstn_tensor5 *vol, const volstn_tensor5 *out, unsigned flags) {
+  int rc = check_host_fused(c, dtype, vol, out);
+  if (rc) return rc;
+  const int64_t B = vol->size[0];
+  if (B == 0 || desc_numel(out) == 0 || !cage_dims)
+    return volstn_b200_cage_warp_forward(dtype, cage, cage_dims, vol, out, flags, nullptr);
+  if (!cage || !vol->data || !out->data) return VOLSTN_ERR_ARG;
+  for (int i = 0; i < 3; i++)
+    if (cage_dims[i] < 1 || cage_dims[i] > 64) return volstn_b200_cage_warp_forward(dtype, cage, cage_dims, vol, out, flags, nullptr);
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t cage_per = (size_t)(3 * cage_dims[0] * cage_dims[1] * cage_dims[2]) * 4;
+  const HostSpan in[2] = {{vol->data, nullptr, sample_elems(vol) * 4, false}, {cage, nullptr, cage_per, false}};
+  const HostSpan outs[1] = {{nullptr, out->data, sample_elems(out) * 4, false}};
+  return run_sliced(c, B, in, 2, outs, 1, 0, [&](int64_t nb, void **din, void **dout, void *, size_t, cudaStream_t st) {
+    volstn_tensor5 tv = rehome(vol, nb, din[0]), to = rehome(out, nb, dout[0]);
+    return volstn_b200_cage_warp_forward(dtype, din[1], cage_dims, &tv, &to, flags, st);
+  });
+}
+
+int volstn_b200_host_cage_warp_backward(volstn_host_ctx *c, int dtype, const void *cage, const int64_t cage_dims[3],
+                                        const volstn_tensor5 *vol, const volstn_tensor5 *gradVol, void *gradCage,
+                                        const volstn_tensor5 *gradOut, unsigned flags) {
+  int rc = check_host_fused(c, dtype, vol, gradOut);
+  if (rc) return rc;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID, ov = flags & VOLSTN_BWD_ONLY_VOLUME;
+  if ((og && ov) || (!og && !gradVol) || (!ov && !gradCage) || !cage_dims) return VOLSTN_ERR_ARG;
+  if (!og && (!desc_contiguous(gradVol) || gradVol->size[0] != vol->size[0])) return VOLSTN_ERR_LAYOUT;
+  for (int i = 0; i < 3; i++)
+    if (cage_dims[i] < 1) return VOLSTN_ERR_SHAPE;
+  for (int i = 0; i < 3; i++)
+    if (cage_dims[i] > 64) return VOLSTN_ERR_UNSUPPORTED;
+  const int64_t B = vol->size[0];
+  if (B == 0) return VOLSTN_OK;
+  if (desc_numel(gradOut) == 0) return VOLSTN_ERR_SHAPE;
+  if (!cage || !vol->data || !gradOut->data) return VOLSTN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (!g.ok) return VOLSTN_ERR_NO_DEVICE;
+  const size_t cage_per = (size_t)(3 * cage_dims[0] * cage_dims[1] * cage_dims[2]) * 4;
+  const HostSpan in[3] = {{vol->data, nullptr, sample_elems(vol) * 4, false}, {cage, nullptr, cage_per, false},
+                          {gradOut->data, nullptr, sample_elems(gradOut) * 4, false}};
+  const HostSpan outs[2] = {{nullptr, og ? nullptr : gradVol->data, og ? 0 : sample_elems(vol) * 4, true},
+                            {nullptr, gradCage, ov ? 0 : cage_per, false}};
+  return run_sliced(c, B, in, 3, outs, 2, 0, [&](int64_t nb, void **din, void **dout, void *, size_t, cudaStream_t st) {
+    volstn_tensor5 tv = rehome(vol, nb, din[0]), tgo = rehome(gradOut, nb, din[2]), tgv;
+    if (!og) tgv = rehome(gradVol, nb, dout[0]);
+    return volstn_b200_cage_warp_backward(dtype, din[1], cage_dims, &tv, og ? nullptr : &tgv, dout[1], &tgo,
+                                          flags & ~VOLSTN_BWD_ZERO_GRADVOL, st);
+  });
 }
 
 static int host_cumsum(volstn_host_ctx *c, int dtype, const void *in, void *out, int64_t B, int N,

@@ -489,16 +489,21 @@ class AffineSamplerVolumetric(Module):
 
     def updateOutput(self, input):
         vol, T = input[0], self._T(input[1])
-        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == T.size(0)
+        assert vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == T.size(0)
         _same_place(vol, T)
         v = _vol_view(vol, self.layout)
         B, C = v.size(0), v.size(4)
         shape = (B, self.depth, self.height, self.width, C) if self.layout == "BDHWC" else (B, C, self.depth, self.height, self.width)
-        out = torch.empty(shape, dtype=vol.dtype, device=vol.device)
-        _require_device(vol.device.index)
-        with torch.cuda.device(vol.device):
-            rc = _abi.lib().volstn_b200_affine_sampler_forward(_dtype_code(vol), T.data_ptr(), _desc(v),
-                                                               _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        out = torch.empty(shape, dtype=vol.dtype, device=vol.device, pin_memory=(not vol.is_cuda and vol.is_pinned()))
+        if vol.is_cuda:
+            _require_device(vol.device.index)
+            with torch.cuda.device(vol.device):
+                rc = _abi.lib().volstn_b200_affine_sampler_forward(_dtype_code(vol), T.data_ptr(), _desc(v),
+                                                                   _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        else:  # host tensors (the loader-side augmentation of dataset_2d.lua:285-311): staged through the GPU
+            assert self.layout == "BDHWC", "host tensors: channels-last only"
+            rc = _abi.lib().volstn_b200_host_affine_sampler_forward(_host_ctx(), _dtype_code(vol), T.data_ptr(), _desc(v),
+                                                                    _desc(out), 0)
         _abi.check(rc, "AffineSamplerVolumetric_updateOutput")
         self.output = out
         return out
@@ -512,17 +517,23 @@ class AffineSamplerVolumetric(Module):
         gv = torch.empty_like(vol)
         gradT = torch.empty((B, 4, 4), dtype=vol.dtype, device=vol.device)
         lib = _abi.lib()
-        ws_bytes = int(lib.volstn_b200_affine_sampler_backward_workspace(B, self.depth, self.height, self.width))
-        ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=vol.device)
         flags = _abi.BWD_ZERO_GRADVOL
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
             gv.zero_()
-        _require_device(vol.device.index)
-        with torch.cuda.device(vol.device):
-            rc = lib.volstn_b200_affine_sampler_backward(_dtype_code(vol), T.data_ptr(), _desc(v), _desc(_vol_view(gv, self.layout)),
-                                                         gradT.data_ptr(), _desc(go), ws.data_ptr(), ws.numel() * 8, flags,
-                                                         _stream(vol))
+        if vol.is_cuda:
+            ws_bytes = int(lib.volstn_b200_affine_sampler_backward_workspace(B, self.depth, self.height, self.width))
+            ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=vol.device)
+            _require_device(vol.device.index)
+            with torch.cuda.device(vol.device):
+                rc = lib.volstn_b200_affine_sampler_backward(_dtype_code(vol), T.data_ptr(), _desc(v),
+                                                             _desc(_vol_view(gv, self.layout)), gradT.data_ptr(), _desc(go),
+                                                             ws.data_ptr(), ws.numel() * 8, flags, _stream(vol))
+        else:
+            assert self.layout == "BDHWC", "host tensors: channels-last only"
+            goc = go if go.is_contiguous() else go.contiguous()
+            rc = lib.volstn_b200_host_affine_sampler_backward(_host_ctx(), _dtype_code(vol), T.data_ptr(), _desc(v), _desc(gv),
+                                                              gradT.data_ptr(), _desc(goc), flags)
         _abi.check(rc, "AffineSamplerVolumetric_updateGradInput")
         self.gradInput = [gv, gradT[0] if input[1].dim() == 2 else gradT]
         return self.gradInput
@@ -558,17 +569,23 @@ class CageWarpVolumetric(Module):
 
     def updateOutput(self, input):
         vol, cage = input[0], self._cage(input[1])
-        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == cage.size(0)
+        assert vol.dim() == 5 and vol.is_contiguous() and vol.size(0) == cage.size(0)
         _same_place(vol, cage)
         v = _vol_view(vol, self.layout)
         B, C = v.size(0), v.size(4)
         d, h, w = self._out_dims(v)
-        out = torch.empty((B, d, h, w, C) if self.layout == "BDHWC" else (B, C, d, h, w), dtype=vol.dtype, device=vol.device)
+        out = torch.empty((B, d, h, w, C) if self.layout == "BDHWC" else (B, C, d, h, w), dtype=vol.dtype, device=vol.device,
+                          pin_memory=(not vol.is_cuda and vol.is_pinned()))
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
-        _require_device(vol.device.index)
-        with torch.cuda.device(vol.device):
-            rc = _abi.lib().volstn_b200_cage_warp_forward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
-                                                          _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        if vol.is_cuda:
+            _require_device(vol.device.index)
+            with torch.cuda.device(vol.device):
+                rc = _abi.lib().volstn_b200_cage_warp_forward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                              _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+        else:
+            assert self.layout == "BDHWC", "host tensors: channels-last only"
+            rc = _abi.lib().volstn_b200_host_cage_warp_forward(_host_ctx(), _dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                               _desc(out), 0)
         _abi.check(rc, "CageWarpVolumetric_updateOutput")
         self.output = out
         return out
@@ -586,11 +603,17 @@ class CageWarpVolumetric(Module):
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
             gv.zero_()
-        _require_device(vol.device.index)
-        with torch.cuda.device(vol.device):
-            rc = _abi.lib().volstn_b200_cage_warp_backward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
-                                                           _desc(_vol_view(gv, self.layout)), gcage.data_ptr(), _desc(go), flags,
-                                                           _stream(vol))
+        if vol.is_cuda:
+            _require_device(vol.device.index)
+            with torch.cuda.device(vol.device):
+                rc = _abi.lib().volstn_b200_cage_warp_backward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                               _desc(_vol_view(gv, self.layout)), gcage.data_ptr(), _desc(go),
+                                                               flags, _stream(vol))
+        else:
+            assert self.layout == "BDHWC", "host tensors: channels-last only"
+            goc = go if go.is_contiguous() else go.contiguous()
+            rc = _abi.lib().volstn_b200_host_cage_warp_backward(_host_ctx(), _dtype_code(vol), cage.data_ptr(), dims, _desc(v),
+                                                                _desc(gv), gcage.data_ptr(), _desc(goc), flags)
         _abi.check(rc, "CageWarpVolumetric_updateGradInput")
         self.gradInput = [gv, gcage]
         return self.gradInput

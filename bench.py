@@ -387,6 +387,7 @@ def run_ours(a):
 
     sweep = run_sweep(a, torch, vnn, synth, _abi) if (a.sweep and rank == 0) else None
     aux = run_aux(a, torch, vnn, synth, _abi, peak) if (rank == 0 and n_gpus == 1 and not a.no_aux) else None
+    fused = run_fused(a, torch, vnn, synth, _abi, peak) if (rank == 0 and n_gpus == 1 and not a.no_aux) else None
 
     # the same step on the other warp-field families (rank 0, inputs resident, context for the headline)
     fields = None
@@ -424,6 +425,8 @@ def run_ours(a):
             line["other_fields"] = fields
         if aux is not None:
             line["aux_kernels"] = aux
+        if fused is not None:
+            line["fused"] = fused
         if sweep is not None:
             line["sweep"] = sweep
         emit(line)
@@ -529,6 +532,156 @@ def run_aux(a, torch, vnn, synth, _abi, peak):
     res["pipeline_32"] = {"ms": ms, "voxels_per_s": Vp / (ms * 1e-3),
                           "workload": f"config 2: Cumsum + grid generator + cage up-sample (8^3 x 4 -> {Np}^3) + source warp, forward and backward, "
                                       f"{Np}^3 x batch {Bp}, CUDA graph replay, L2 flushed before each replay"}
+    return res
+
+
+def run_fused(a, torch, vnn, synth, _abi, peak):
+    """SURVEY section 8 rows f1-f3 (rank 0, N=1): each fused / in-place module next to the chain of un-fused
+    modules it replaces, same inputs, same results (tests/test_gpu_rowwarp.py), device-resident, K launches back to
+    back between two CUDA events.  `bytes_per_voxel` are ALGORITHMIC bytes of the chain and of the fused call."""
+    N, B, K = a.size, a.batch, max(5, min(a.steps, 20))
+    V = B * N ** 3
+    res = {"note": f"{N}^3 x batch {B}, C=1, fp32; ms per call; working sets exceed L2 (no flush) except pipeline_32 (flushed)"}
+    rng = np.random.default_rng(11)
+    nb = min(B, 8)
+
+    def rep(x):
+        return torch.from_numpy(x).cuda().repeat(B // nb, *([1] * (x.ndim - 1))).contiguous()
+
+    def timed(fn, k=K):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    vol = rep(synth.volume("v2", nb, N, N, N, 1, rng))
+    go = torch.randn((B, N, N, N, 1), device="cuda")
+
+    # ---- f1: cage up-sample + source warp ------------------------------------------------------------------
+    csz = 8
+    cage = torch.from_numpy(synth.alignet_cage(nb, csz, rng).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
+    cage_vol = torch.ones((B, csz, csz, csz, 4), device="cuda")
+    cage_vol[..., :3] = cage.permute(0, 2, 3, 4, 1)
+    field_i = vnn.VolumetricGridGenerator(N, N, N).updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))
+    up, warp = vnn.BilinearSamplerVolumetric(onlyVolume=True), vnn.BilinearSamplerVolumetric(onlyGrid=True)
+    fus = vnn.CageWarpVolumetric(onlyGrid=True)
+    field = up.updateOutput([cage_vol, field_i])
+    _, gfield = warp.updateGradInput([vol, field], go)
+    c_f = timed(lambda: (up.updateOutput([cage_vol, field_i]), warp.updateOutput([vol, field])))
+    c_b = timed(lambda: (warp.updateGradInput([vol, field], go), up.updateGradInput([cage_vol, field_i], gfield)), k=3)
+    f_f = timed(lambda: fus.updateOutput([vol, cage]))
+    f_b = timed(lambda: fus.updateGradInput([vol, cage], go))
+    res["cage_warp"] = {
+        "what": "models/alignet_2d.lua:136-147 lifted to 3-D: cage 8^3 x 3 -> field -> warp; backward to the cage only (source is data)",
+        "chain": {"fwd_ms": c_f, "bwd_ms": c_b, "voxels_per_s": V / ((c_f + c_b) * 1e-3), "bytes_per_voxel": 56 + 72,
+                  "calls": "sampler fwd (C=4 cage volume, constant identity field) + sampler fwd; sampler bwd onlyGrid + sampler bwd onlyVolume"},
+        "fused": {"fwd_ms": f_f, "bwd_ms": f_b, "voxels_per_s": V / ((f_f + f_b) * 1e-3), "bytes_per_voxel": 8 + 8,
+                  "calls": "volstn_b200_cage_warp_forward + _backward (ONLY_GRID)"},
+        "speedup_fwd": c_f / f_f, "speedup_bwd": c_b / f_b, "speedup_step": (c_f + c_b) / (f_f + f_b),
+        "hbm_not_allocated_mib": 2 * V * 16 / 2 ** 20}
+    del field, field_i, gfield, cage_vol
+
+    # ---- f3: grid generator folded into the sampler ----------------------------------------------------------
+    T = torch.eye(4, device="cuda").repeat(B, 1, 1) + 0.02 * torch.randn(B, 4, 4, device="cuda")
+    gen, smp, afs = vnn.VolumetricGridGenerator(N, N, N), vnn.BilinearSamplerVolumetric(), vnn.AffineSamplerVolumetric(N, N, N)
+    grid = gen.updateOutput(T)
+    _, gg = smp.updateGradInput([vol, grid], go)
+    c_f = timed(lambda: smp.updateOutput([vol, gen.updateOutput(T)]))
+    c_b = timed(lambda: gen.updateGradInput(T, smp.updateGradInput([vol, grid], go)[1]))
+    f_f = timed(lambda: afs.updateOutput([vol, T]))
+    f_b = timed(lambda: afs.updateGradInput([vol, T], go))
+    res["affine_sampler"] = {
+        "what": "the projector of stn3dtorch/test.lua:15-25: VolumetricGridGenerator + BilinearSamplerVolumetric",
+        "chain": {"fwd_ms": c_f, "bwd_ms": c_b, "voxels_per_s": V / ((c_f + c_b) * 1e-3), "bytes_per_voxel": 40 + 60},
+        "fused": {"fwd_ms": f_f, "bwd_ms": f_b, "voxels_per_s": V / ((f_f + f_b) * 1e-3), "bytes_per_voxel": 8 + 12},
+        "speedup_fwd": c_f / f_f, "speedup_bwd": c_b / f_b, "speedup_step": (c_f + c_b) / (f_f + f_b)}
+    del grid, gg
+
+    # the same through the HOST entry points (the loader-side augmentation runs on CPU tensors, dataset_2d.lua:285-311)
+    if not a.no_e2e:
+        Bh = min(B, 16)
+        vol_h = vol[:Bh].cpu().pin_memory()
+        T_h = T[:Bh].cpu().pin_memory()
+        gen_h, smp_h, afs_h = vnn.VolumetricGridGenerator(N, N, N), vnn.BilinearSamplerVolumetric(reuseForwardInputs=False), vnn.AffineSamplerVolumetric(N, N, N)
+
+        def wall(fn, k=3):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / k * 1e3
+
+        ch = wall(lambda: smp_h.updateOutput([vol_h, gen_h.updateOutput(T_h)]))
+        fu = wall(lambda: afs_h.updateOutput([vol_h, T_h]))
+        Vh = Bh * N ** 3
+        res["affine_sampler"]["host_forward"] = {
+            "batch": Bh, "chain_ms": ch, "fused_ms": fu, "speedup": ch / fu,
+            "chain_pcie_bytes": Vh * (16 + 4 + 16 + 4), "fused_pcie_bytes": Vh * 8 + Bh * 64,
+            "path": "pinned host tensors in, host tensors out: host_gridgen_forward + host_sampler_forward vs host_affine_sampler_forward"}
+
+    # ---- f2: channel-first tensors in place --------------------------------------------------------------------
+    C = 4
+    Bc = max(1, B // C)
+    Vc = Bc * N ** 3
+    volc = torch.randn((Bc, C, N, N, N), device="cuda")
+    goc = torch.randn((Bc, C, N, N, N), device="cuda")
+    gridc = rep(synth.grid("g2", nb, N, N, N, rng))[:Bc].permute(0, 4, 1, 2, 3).contiguous()
+    cfm, clm = vnn.BilinearSamplerVolumetric(layout="BCDHW"), vnn.BilinearSamplerVolumetric()
+    cl = lambda t: t.permute(0, 2, 3, 4, 1).contiguous()          # nn.Transpose = materialised copy (nn/Transpose.lua)
+    cf = lambda t: t.permute(0, 4, 1, 2, 3).contiguous()
+    c_f = timed(lambda: cf(clm.updateOutput([cl(volc), cl(gridc)])))
+    c_b = timed(lambda: [cf(g) for g in clm.updateGradInput([cl(volc), cl(gridc)], cl(goc))], k=3)
+    f_f = timed(lambda: cfm.updateOutput([volc, gridc]))
+    f_b = timed(lambda: cfm.updateGradInput([volc, gridc], goc), k=3)
+    res["channel_first"] = {
+        "what": f"B x C x D x H x W tensors (C={C}, batch {Bc}, ALIGNet-like field g2): nn.Transpose copies + packed sampler vs the row kernels on permuted views",
+        "chain": {"fwd_ms": c_f, "bwd_ms": c_b, "voxels_per_s": Vc / ((c_f + c_b) * 1e-3)},
+        "in_place": {"fwd_ms": f_f, "bwd_ms": f_b, "voxels_per_s": Vc / ((f_f + f_b) * 1e-3),
+                     "fwd_frac_of_hbm_peak": fwd_bytes(C) * Vc / (f_f * 1e-3) / 1e9 / peak,
+                     "bwd_frac_of_hbm_peak": bwd_bytes(C) * Vc / (f_b * 1e-3) / 1e9 / peak},
+        "speedup_fwd": c_f / f_f, "speedup_bwd": c_b / f_b, "speedup_step": (c_f + c_b) / (f_f + f_b)}
+    del volc, goc, gridc
+
+    # ---- BASELINE.json config 2 with the fused module: Cumsum -> +beta -> CageWarp, forward and backward ---------
+    Np, Bp = 32, 32
+    delta = 2.0 / (csz - 1)
+    dd = torch.from_numpy(np.abs(delta * (1 + 0.25 * rng.standard_normal((Bp, 3, csz, csz, csz)))).astype(np.float32)).cuda()
+    src = torch.from_numpy(synth.volume("v2", Bp, Np, Np, Np, 1, rng)).cuda()
+    gop = torch.from_numpy(synth.grad_output(Bp, Np, Np, Np, 1, rng)).cuda()
+    csp, cw = vnn.Cumsum(), vnn.CageWarpVolumetric(onlyGrid=True)
+
+    def pipeline():
+        cage_p = csp.updateOutput(dd) + (-1.0 - delta)
+        cw.updateOutput([src, cage_p])
+        _, gcage = cw.updateGradInput([src, cage_p], gop)
+        csp.updateGradInput(dd, gcage)
+
+    for _ in range(3):
+        pipeline()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        pipeline()
+    g.replay()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    res["pipeline_32_fused"] = {"ms": ms, "voxels_per_s": Bp * Np ** 3 / (ms * 1e-3),
+                                "workload": f"config 2 with the fused module: Cumsum + beta + CageWarpVolumetric forward, backward to the cage, "
+                                            f"Cumsum backward; {Np}^3 x batch {Bp}, CUDA graph replay, L2 flushed before each replay"}
     return res
 
 

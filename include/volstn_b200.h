@@ -219,6 +219,18 @@ int volstn_b200_host_gridgen_forward(volstn_host_ctx *ctx, int dtype, const void
                                      int64_t D, int64_t H, int64_t W);
 int volstn_b200_host_gridgen_backward(volstn_host_ctx *ctx, int dtype, const void *gradGrid, void *gradT,
                                       int64_t B, int64_t D, int64_t H, int64_t W);
+/* the fused modules on HOST tensors (contiguous, float): see volstn_b200_affine_sampler_* / volstn_b200_cage_warp_*.
+ * gradVol is always zero-filled first (the module's :zero()); workspace is owned by the context. */
+int volstn_b200_host_affine_sampler_forward(volstn_host_ctx *ctx, int dtype, const void *T, const volstn_tensor5 *vol,
+                                            const volstn_tensor5 *out, unsigned flags);
+int volstn_b200_host_affine_sampler_backward(volstn_host_ctx *ctx, int dtype, const void *T, const volstn_tensor5 *vol,
+                                             const volstn_tensor5 *gradVol, void *gradT,
+                                             const volstn_tensor5 *gradOut, unsigned flags);
+int volstn_b200_host_cage_warp_forward(volstn_host_ctx *ctx, int dtype, const void *cage, const int64_t cage_dims[3],
+                                       const volstn_tensor5 *vol, const volstn_tensor5 *out, unsigned flags);
+int volstn_b200_host_cage_warp_backward(volstn_host_ctx *ctx, int dtype, const void *cage, const int64_t cage_dims[3],
+                                        const volstn_tensor5 *vol, const volstn_tensor5 *gradVol, void *gradCage,
+                                        const volstn_tensor5 *gradOut, unsigned flags);
 int volstn_b200_host_cumsum_forward(volstn_host_ctx *ctx, int dtype, const void *in, void *out, int64_t B,
                                     int N, const int64_t *dims);
 int volstn_b200_host_cumsum_backward(volstn_host_ctx *ctx, int dtype, const void *gradOut, void *gradIn,

@@ -287,3 +287,40 @@ def test_fused_modules_reject_what_they_do_not_support():
     assert lib.volstn_b200_cage_warp_forward(_abi.F32, cage.data_ptr(), dims, d(vf), d(of), 0, stream()) == _abi.ERR_UNSUPPORTED
     o1 = torch.zeros((1, 1, 4, 4, 1), device="cuda")      # extent 1: the generator asserts depth > 1 (lua:6-8)
     assert lib.volstn_b200_affine_sampler_forward(_abi.F32, T.float().data_ptr(), d(vf), d(o1), 0, stream()) == _abi.ERR_SHAPE
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused modules on HOST tensors (the loader-side augmentation of dataset_2d.lua:285-311 runs on CPU tensors)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("B", [1, 37])
+def test_host_fused_modules_match_device_and_oracle(pinned, B):
+    rng = np.random.default_rng(71 + B)
+    oshape, C = (9, 12, 34), 1
+    vol = synth.volume("v1", B, 8, 10, 12, C, rng)
+    T = random_affine(B, rng)
+    go = synth.grad_output(B, *oshape, C, rng)
+    cage = synth.alignet_cage(B, 4, rng).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).pin_memory() if pinned else torch.from_numpy(a)
+    # affine
+    grid = oracle.gridgen_forward(T, *oshape, accumulate=np.float32)
+    dev_grid = host(vnn.VolumetricGridGenerator(*oshape).updateOutput(dev(T)))
+    ref_out = oracle.sampler_forward(vol, dev_grid)
+    ref_gv, ref_gg = oracle.sampler_backward(vol, dev_grid, go)
+    m = vnn.AffineSamplerVolumetric(*oshape)
+    out = m.updateOutput([t(vol), t(T)])
+    assert not out.is_cuda and bits_equal(out.numpy(), ref_out)
+    gv, gT = m.updateGradInput([t(vol), t(T)], t(go))
+    assert max_rel(gv.numpy(), ref_gv) <= 1e-4 and max_rel(gT.numpy(), oracle.gridgen_backward(ref_gg)) <= 1e-5
+    assert np.abs(grid - dev_grid).max() <= 1e-6
+    # cage
+    src = synth.volume("v1", B, *oshape, C, rng)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    mc = vnn.CageWarpVolumetric()
+    out = mc.updateOutput([t(src), t(cage)])
+    assert not out.is_cuda and bits_equal(out.numpy(), ref_out)
+    gsrc, gcage = mc.updateGradInput([t(src), t(cage)], t(go))
+    assert max_rel(gsrc.numpy(), ref_gsrc) <= 1e-4 and max_rel(gcage.numpy(), ref_gcage) <= 1e-4
+    mo = vnn.CageWarpVolumetric(onlyGrid=True)
+    gsrc2, gcage2 = mo.updateGradInput([t(src), t(cage)], t(go))
+    assert float(gsrc2.abs().max()) == 0.0 and max_rel(gcage2.numpy(), ref_gcage) <= 1e-4
