@@ -313,4 +313,59 @@ int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t ca
   return row_backward(a, p, a.s.B, og, ov, st);
 }
 
+// =============================================================================================
+// f4: the training step of the cage warp in one pass -- forward, SmoothL1Criterion (model.lua:34), its gradient,
+// the IoU counts of util.lua:110-120 and the backward to the cage
+// =============================================================================================
+int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
+                               const volstn_tensor5 *target, const volstn_tensor5 *out, const volstn_tensor5 *gradVol,
+                               void *gradCage, double *loss_sum, uint64_t *iou_counts, float grad_scale, unsigned flags,
+                               void *cuda_stream) {
+  int rc = check_fused(dtype, vol, target);
+  if (rc) return rc;
+  if ((rc = check_cage(cage_dims))) return rc;
+  if (flags & VOLSTN_BWD_ONLY_VOLUME) return VOLSTN_ERR_ARG;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID;
+  if (vol->size[4] != 1) return VOLSTN_ERR_UNSUPPORTED;  // single-channel volumes (ALIGNet's occupancy grids)
+  if (target->size[1] < 2 || target->size[2] < 2 || target->size[3] < 2) return VOLSTN_ERR_SHAPE;
+  if (out)
+    for (int i = 0; i < 5; i++)
+      if (out->size[i] != target->size[i] || (target->size[i] > 1 && out->stride[i] != target->stride[i]))
+        return VOLSTN_ERR_LAYOUT;  // the optional forward output shares the target's layout
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int64_t B = vol->size[0];
+  if (!og) {
+    if (!gradVol) return VOLSTN_ERR_ARG;
+    for (int i = 0; i < 5; i++)
+      if (gradVol->size[i] != vol->size[i]) return VOLSTN_ERR_SHAPE;
+    if ((flags & VOLSTN_BWD_ZERO_GRADVOL) && desc_numel(gradVol) && (rc = zero_grad_vol(gradVol, st))) return rc;
+  }
+  if (B == 0) return VOLSTN_OK;
+  if (!gradCage || !loss_sum) return VOLSTN_ERR_ARG;
+  const size_t cage_bytes = (size_t)B * 3 * cage_dims[0] * cage_dims[1] * cage_dims[2] * 4;
+  VOLSTN_CUDA_TRY(cudaMemsetAsync(gradCage, 0, cage_bytes, st));
+  VOLSTN_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, (size_t)B * sizeof(double), st));
+  if (iou_counts) VOLSTN_CUDA_TRY(cudaMemsetAsync(iou_counts, 0, (size_t)B * 2 * sizeof(uint64_t), st));
+  if (desc_numel(target) == 0) return VOLSTN_OK;
+  if (!cage || (out && !out->data)) return VOLSTN_ERR_ARG;
+  RowArgs a;
+  RowPlan p;
+  zero_args(a);
+  memset(&p, 0, sizeof(p));
+  p.src = ROW_SRC_CAGE;
+  if (!plan_volume(a, p, vol, target, og ? nullptr : gradVol)) return VOLSTN_ERR_LAYOUT;
+  if (!p.c1) return VOLSTN_ERR_LAYOUT;
+  a.s.gout = static_cast<const float *>(target->data);
+  a.s.out = out ? static_cast<float *>(out->data) : nullptr;
+  a.cage = static_cast<const float *>(cage);
+  a.gcage = static_cast<float *>(gradCage);
+  a.cD = (int)cage_dims[0], a.cH = (int)cage_dims[1], a.cW = (int)cage_dims[2];
+  a.loss_norm = grad_scale;
+  a.loss = loss_sum;
+  a.iou = reinterpret_cast<unsigned long long *>(iou_counts);
+  plan_debug_flags(a, flags);
+  plan_geometry(a, p);
+  return row_cage_step(a, p, a.s.B, og, st);
+}
+
 }  // extern "C"

@@ -237,26 +237,37 @@ __device__ __forceinline__ void row_voxel_forward(const RowArgs &a, const VoxelS
 }
 
 // returns the gradient of the three coordinates (before any sink)
-template <bool C1, bool OG, bool OV, int MODE>
+// LOSS (single channel, fused training step): `gop` points at the TARGET voxel; the forward value is formed from the
+// gathers that the backward needs anyway, gradOut is the SmoothL1 gradient norm * clamp(out - target, -1, 1)
+// (THNN SmoothL1Criterion_updateGradInput) and (out, target) are handed back for the loss / IoU accumulators.
+template <bool C1, bool OG, bool OV, int MODE, bool LOSS = false>
 __device__ __forceinline__ void row_voxel_backward(const RowArgs &a, const VoxelSetup<float> &s, const float *__restrict__ vb,
                                                    long long gv_delta, const float *__restrict__ gop, bool valid,
-                                                   float &gz, float &gy, float &gx) {
+                                                   float &gz, float &gy, float &gx, float *fwd = nullptr,
+                                                   float *tgt = nullptr) {
+  static_assert(!LOSS || (C1 && !OV), "the fused step is single-channel and needs the gathers");
   constexpr bool FAST = MODE == 1;
   const int sW = C1 ? 1 : a.vW;
   float cw[8];
-  if constexpr (!OG) s.corner_weights(cw);
+  if constexpr (!OG || LOSS) s.corner_weights(cw);
   const CornerRows<float> rows(vb, MODE ? s.fbase : s.base32(a.vD, a.vH, sW), a.vD, a.vH);
   float dot[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) dot[k] = 0.f;
   const int C = C1 ? 1 : a.s.C;
   for (int t = 0; t < C; t++) {
-    const float go = ld_stream_f1(gop + (C1 ? 0 : t * a.osC));
+    float go = ld_stream_f1(gop + (C1 ? 0 : t * a.osC));
     const int co = C1 ? 0 : t * a.vC;
     if constexpr (!OV) {
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = (FAST || s.in(k)) ? __ldg(rows.p[k >> 1] + ((k & 1) ? sW : 0) + co) : 0.f;
+      if constexpr (LOSS) {
+        const float o = sum8<0>(cw, v);  // the forward value, bit for bit (...c:566-573)
+        const float x = __fsub_rn(o, go);
+        *fwd = o, *tgt = go;
+        go = x < -1.0f ? -a.loss_norm : (x > 1.0f ? a.loss_norm : __fmul_rn(a.loss_norm, x));
+      }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const float d = __fadd_rn(dot[k], __fmul_rn(v[k], go));  // dot += v * go (...c:736)
@@ -424,7 +435,7 @@ struct CageAcc {
   }
 };
 
-template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV>
+template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false>
 __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];
@@ -451,6 +462,10 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_ro
   cacc.reset();
   const int owp = row_owp(a);
   float *st = (SRC == ROW_SRC_CAGE && SINK) ? m.stage + wid * (TWO_ROWS ? 2 : 1) * 6 * owp : nullptr;
+  // fused step: SmoothL1 sum of this lane (THNN accumulates in double) and the IoU counts of this warp
+  double lsum = 0.0;
+  unsigned n_inter = 0, n_union = 0;
+  float *outb = (LOSS && s.out) ? opaque(s.out + (long long)b * a.oB) : nullptr;
 
   int r = (blockIdx.x * kRowWarps + wid) * a.rows_per_warp;
   const int r_end = min(r + a.rows_per_warp, s.oD * s.oH);
@@ -470,24 +485,40 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_ro
       const float *gop[2];
 #pragma unroll
       for (int v = 0; v < 2; v++) gop[v] = gob + sl[v].z * a.osD + sl[v].y * a.osH + sl[v].x * a.osW;
-      float gz[2], gy[2], gx[2];
+      float gz[2], gy[2], gx[2], fo[2], ft[2];
       if (__all_sync(0xffffffffu, tier == 2)) {
 #pragma unroll
         for (int v = 0; v < 2; v++) su[v].template finish_fast<false>(s, a.vD, a.vH, sW);
 #pragma unroll
         for (int v = 0; v < 2; v++)
-          row_voxel_backward<C1, OG, OV, 1>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v]);
+          row_voxel_backward<C1, OG, OV, 1, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
       } else if (__all_sync(0xffffffffu, tier >= 1)) {
 #pragma unroll
         for (int v = 0; v < 2; v++) su[v].template finish_fast<true>(s, a.vD, a.vH, sW);
 #pragma unroll
         for (int v = 0; v < 2; v++)
-          row_voxel_backward<C1, OG, OV, 2>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v]);
+          row_voxel_backward<C1, OG, OV, 2, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
       } else {
 #pragma unroll
         for (int v = 0; v < 2; v++) {
           su[v].finish_exact(s);
-          row_voxel_backward<C1, OG, OV, 0>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v]);
+          row_voxel_backward<C1, OG, OV, 0, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
+        }
+      }
+      if constexpr (LOSS) {
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+          const bool ok = sl[v].valid;
+          if (ok) {
+            // SmoothL1Criterion_updateOutput: z = |input - target|; sum += z < 1 ? 0.5 z^2 : z - 0.5  (double)
+            const double zz = (double)fabsf(__fsub_rn(fo[v], ft[v]));
+            lsum += zz < 1.0 ? 0.5 * zz * zz : zz - 0.5;
+            if (outb) st_stream_f1(outb + sl[v].z * a.osD + sl[v].y * a.osH + sl[v].x * a.osW, fo[v]);
+          }
+          // computeIOU (util.lua:110-120): thresholds at 0.5, intersection and union counts per sample
+          const bool p = ok && fo[v] > 0.5f, q = ok && ft[v] > 0.5f;
+          n_inter += __popc(__ballot_sync(0xffffffffu, p && q));
+          n_union += __popc(__ballot_sync(0xffffffffu, p || q));
         }
       }
       // ---- sinks of the coordinate gradient ----
@@ -542,6 +573,17 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_ro
     }
   }
 
+  if constexpr (LOSS) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if (lane == 0) {
+      atomicAdd(a.loss + b, lsum);
+      if (a.iou) {
+        atomicAdd(a.iou + 2 * b, (unsigned long long)n_inter);
+        atomicAdd(a.iou + 2 * b + 1, (unsigned long long)n_union);
+      }
+    }
+  }
   if constexpr (SRC == ROW_SRC_AFFINE && SINK) {
     // warp tree in double, then the warps in order: one partial 4x4 per CTA (row 3 is zero: gradGrid[...,3] = 0)
 #pragma unroll
@@ -620,10 +662,10 @@ int launch_fwd(const RowArgs &a, int B, cudaStream_t st) {
   return VOLSTN_OK;
 }
 
-template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV>
+template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV, bool LOSS = false>
 int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
   const size_t smem = row_smem_bytes<SRC, true>(a, TWO);
-  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV>, smem);
+  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS>, smem);
   if (rc) return rc;
   for (int b0 = 0; b0 < B; b0 += 65535) {
     RowArgs c = a;
@@ -637,7 +679,10 @@ int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
     if (c.partial) c.partial += (long long)b0 * a.nblk * 16;
     if (c.cage) c.cage += (long long)b0 * 3 * a.cD * a.cH * a.cW;
     if (c.gcage) c.gcage += (long long)b0 * 3 * a.cD * a.cH * a.cW;
-    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
+    if (c.s.out) c.s.out += (long long)b0 * a.oB;
+    if (c.loss) c.loss += b0;
+    if (c.iou) c.iou += 2 * (long long)b0;
+    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
     if ((rc = after_launch())) return rc;
   }
   return VOLSTN_OK;
@@ -711,6 +756,16 @@ int row_backward(const RowArgs &a, const RowPlan &p, int B, bool og, bool ov, cu
       return VOLSTN_OK;
     default: return bwd_mode<ROW_SRC_CAGE, false>(a, p, B, og, ov, st);
   }
+}
+
+// fused training step of the cage warp: forward + SmoothL1 + backward in one pass (single channel)
+int row_cage_step(const RowArgs &a, const RowPlan &p, int B, bool og, cudaStream_t st) {
+  if (!p.c1 || p.src != ROW_SRC_CAGE) return VOLSTN_ERR_UNSUPPORTED;
+  if (og)
+    return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, true, false, true>(a, B, st)
+                      : launch_bwd<ROW_SRC_CAGE, false, true, false, true, false, true>(a, B, st);
+  return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, false, false, true>(a, B, st)
+                    : launch_bwd<ROW_SRC_CAGE, false, true, false, false, false, true>(a, B, st);
 }
 
 }  // namespace volstn

@@ -37,6 +37,10 @@ struct RowArgs {
   float *gcage;              // ROW_SRC_CAGE backward: same shape, accumulated into
   int cD, cH, cW;
   float *gradT;              // ROW_SRC_AFFINE backward: B x 4 x 4 (row 3 is zero)
+  // fused training step (k_row_bwd<..., LOSS>): s.gout is the TARGET, s.out (optional) receives the forward value
+  float loss_norm;           // SmoothL1 gradient scale: 1 / nElement (sizeAverage) or 1
+  double *loss;              // B sums of the SmoothL1 terms (accumulated into)
+  unsigned long long *iou;   // B x 2 (intersection, union) counts at threshold 0.5 (accumulated into), may be null
   int g3;                    // ROW_SRC_GRID: grid width 3 (forward corner order of ...c:149-156, no 4th gradGrid component)
 };
 
@@ -53,5 +57,6 @@ struct RowPlan {
 void row_geometry(int64_t B, int64_t rows, int src, int two_rows, int *nblk, int *rows_per_warp);
 int row_forward(const RowArgs &a, const RowPlan &p, int B, cudaStream_t st);
 int row_backward(const RowArgs &a, const RowPlan &p, int B, bool only_grid, bool only_vol, cudaStream_t st);
+int row_cage_step(const RowArgs &a, const RowPlan &p, int B, bool only_grid, cudaStream_t st);
 
 }  // namespace volstn

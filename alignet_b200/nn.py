@@ -30,7 +30,7 @@ from . import _abi
 from ._abi import Tensor5
 
 __all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
-           "AffineSamplerVolumetric", "CageWarpVolumetric"]
+           "AffineSamplerVolumetric", "CageWarpVolumetric", "CageWarpSmoothL1Volumetric"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -617,3 +617,66 @@ class CageWarpVolumetric(Module):
         _abi.check(rc, "CageWarpVolumetric_updateGradInput")
         self.gradInput = [gv, gcage]
         return self.gradInput
+
+
+class CageWarpSmoothL1Volumetric(Module):
+    """One training step of ALIGNet's warp head in ONE kernel:
+
+        output   = CageWarpVolumetric:forward({source, cage})
+        loss     = nn.SmoothL1Criterion():forward(output, target)          (model.lua:34, train.lua:123)
+        gradOut  = criterion:backward(output, target)
+        gradInput = CageWarpVolumetric:backward({source, cage}, gradOut)   (train.lua:125-126)
+        iou      = computeIOU(output, target)                              (util.lua:110-120)
+
+    Neither ``output`` nor ``gradOut`` has to exist: the kernel reads the source gathers and the target
+    (8 B/voxel).  ``forwardBackward({source, cage}, target)`` returns ``(loss, gradInput)``; ``loss`` is a 0-dim
+    float64 CUDA tensor (no host synchronisation), ``self.lossPerSample`` the per-sample sums, ``self.iouCounts``
+    the exact ``B x 2`` (intersection, union) counts, ``self.output`` the warped volume if ``keepOutput``.
+    Single-channel ``B x D x H x W x 1`` CUDA float volumes."""
+
+    def __init__(self, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False):
+        super().__init__()
+        self.sizeAverage, self.onlyGrid, self.keepOutput = sizeAverage, onlyGrid, keepOutput
+        self.gradInput = []
+        self.loss = self.lossPerSample = self.iouCounts = None
+
+    def forwardBackward(self, input, target):
+        vol, cage = input[0], CageWarpVolumetric._cage(input[1])
+        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(4) == 1 and vol.size(0) == cage.size(0)
+        assert target.dim() == 5 and target.size(0) == vol.size(0) and target.size(4) == 1
+        _same_place(vol, cage, target)
+        B = vol.size(0)
+        n = target.numel()
+        out = torch.empty(tuple(target.shape), dtype=vol.dtype, device=vol.device).as_strided(target.shape, target.stride()) \
+            if self.keepOutput and target.is_contiguous() else None
+        if self.keepOutput and out is None:
+            target = target.contiguous()
+            out = torch.empty_like(target)
+        gv = torch.empty_like(vol)
+        gcage = torch.empty_like(cage)
+        loss_sum = torch.empty((B,), dtype=torch.float64, device=vol.device)
+        iou = torch.empty((B, 2), dtype=torch.int64, device=vol.device)
+        # THNN: norm = sizeAverage ? 1. / ((real)nElement) : 1.  (double division, stored in `real`)
+        norm = float(torch.tensor(1.0 / float(torch.tensor(float(n), dtype=torch.float32)), dtype=torch.float32)) if self.sizeAverage else 1.0
+        dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
+        flags = _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gv.zero_()
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_cage_warp_step(_dtype_code(vol), cage.data_ptr(), dims, _desc(vol), _desc(target),
+                                                       _desc(out) if out is not None else None, _desc(gv), gcage.data_ptr(),
+                                                       loss_sum.data_ptr(), iou.data_ptr(), ctypes.c_float(norm), flags,
+                                                       _stream(vol))
+        _abi.check(rc, "CageWarpSmoothL1Volumetric_forwardBackward")
+        self.lossPerSample, self.iouCounts = loss_sum, iou
+        self.loss = loss_sum.sum() / n if self.sizeAverage else loss_sum.sum()
+        self.output = out if out is not None else torch.empty(0)
+        self.gradInput = [gv, gcage]
+        return self.loss, self.gradInput
+
+    def iou(self):
+        """computeIOU (util.lua:118-119): mean over the batch of intersection / union"""
+        c = self.iouCounts.to(torch.float64)
+        return (c[:, 0] / c[:, 1]).sum() / c.size(0)

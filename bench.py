@@ -587,6 +587,27 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         "hbm_not_allocated_mib": 2 * V * 16 / 2 ** 20}
     del field, field_i, gfield, cage_vol
 
+    # ---- f4: the whole training step of the warp head (forward + SmoothL1 + IoU + backward) in one kernel ----------
+    target = rep(synth.volume("v2", nb, N, N, N, 1, rng))
+    step = vnn.CageWarpSmoothL1Volumetric()
+
+    def chain_step():   # the fused modules + the criterion as separate passes (torch's smooth_l1 as the stand-in for THNN)
+        o = fus.updateOutput([vol, cage])
+        x = o - target
+        loss = torch.where(x.abs() < 1, 0.5 * x * x, x.abs() - 0.5).sum()
+        g_o = x.clamp(-1, 1) / o.numel()
+        fus.updateGradInput([vol, cage], g_o)
+        return loss
+
+    c_s = timed(chain_step)
+    f_s = timed(lambda: step.forwardBackward([vol, cage], target))
+    res["cage_warp_step"] = {
+        "what": "model:forward + SmoothL1Criterion:forward/backward + computeIOU + model:backward (train.lua:123-126, model.lua:34, util.lua:110-120), backward to the cage",
+        "fused_modules_plus_elementwise_criterion_ms": c_s, "one_kernel_ms": f_s, "speedup": c_s / f_s,
+        "voxels_per_s": V / (f_s * 1e-3), "bytes_per_voxel": 8,
+        "vs_unfused_module_chain": (res["cage_warp"]["chain"]["fwd_ms"] + res["cage_warp"]["chain"]["bwd_ms"] + (c_s - f_f - f_b)) / f_s}
+    del target
+
     # ---- f3: grid generator folded into the sampler ----------------------------------------------------------
     T = torch.eye(4, device="cuda").repeat(B, 1, 1) + 0.02 * torch.randn(B, 4, 4, device="cuda")
     gen, smp, afs = vnn.VolumetricGridGenerator(N, N, N), vnn.BilinearSamplerVolumetric(), vnn.AffineSamplerVolumetric(N, N, N)

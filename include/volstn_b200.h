@@ -159,6 +159,22 @@ int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t ca
                                    const volstn_tensor5 *gradVol, void *gradCage, const volstn_tensor5 *gradOut,
                                    unsigned flags, void *cuda_stream);
 
+/* The training step of the cage warp in ONE pass (single-channel volumes):
+ *     out      = cage_warp_forward(cage, vol)                                   (optionally stored: `out` may be NULL)
+ *     loss_sum[b] = sum over the voxels of sample b of SmoothL1(out - target)     (nn.SmoothL1Criterion, model.lua:34:
+ *                   z = |x|, z < 1 ? 0.5 z^2 : z - 0.5, accumulated in double like THNN's accreal; NOT yet divided)
+ *     gradOut  = grad_scale * clamp(out - target, -1, 1)                        (SmoothL1Criterion_updateGradInput;
+ *                   grad_scale = 1 / nElement for sizeAverage = true, the Torch default)
+ *     gradVol, gradCage = cage_warp_backward(gradOut)                           (gradCage assigned, gradVol as usual)
+ *     iou_counts[b] = {#(out > 0.5 and target > 0.5), #(out > 0.5 or target > 0.5)}   (computeIOU, util.lua:110-120;
+ *                   exact integer counts, may be NULL)
+ * Neither `out` nor gradOut ever has to exist in memory: the step reads the source gathers and the target (8 B/voxel).
+ * `out`, when given, must have the target's shape and strides. */
+int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
+                               const volstn_tensor5 *target, const volstn_tensor5 *out, const volstn_tensor5 *gradVol,
+                               void *gradCage, double *loss_sum, uint64_t *iou_counts, float grad_scale, unsigned flags,
+                               void *cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Grid generator (nn.VolumetricGridGenerator), DEVICE pointers, contiguous tensors
  * ------------------------------------------------------------------------------------------- */

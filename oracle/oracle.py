@@ -253,6 +253,31 @@ def gridgen_backward(grad_grid: np.ndarray, accumulate=np.float64) -> np.ndarray
 
 
 # --------------------------------------------------------------------------------------------
+# nn.SmoothL1Criterion (model.lua:34) and computeIOU (util.lua:110-120) -- parity UNPINNED: the criterion lives in
+# Torch7's THNN (generic/SmoothL1Criterion.c), which is not vendored; restated from its published algorithm:
+#   updateOutput   : z = |input - target| ; sum += z < 1 ? 0.5 z^2 : z - 0.5  (accreal = double) ; sum /= nElement
+#   updateGradInput: x = input - target ; grad = x < -1 ? -norm : x > 1 ? norm : norm * x ; norm = 1 / nElement
+# --------------------------------------------------------------------------------------------
+def smooth_l1_forward(inp: np.ndarray, target: np.ndarray, size_average: bool = True) -> float:
+    z = np.abs(inp - target).astype(np.float64)       # the subtraction happens in `real`, the sum in double
+    s = float(np.sum(np.where(z < 1.0, 0.5 * z * z, z - 0.5)))
+    return s / inp.size if size_average else s
+
+
+def smooth_l1_backward(inp: np.ndarray, target: np.ndarray, size_average: bool = True) -> np.ndarray:
+    norm = inp.dtype.type(1.0 / float(inp.dtype.type(inp.size))) if size_average else inp.dtype.type(1.0)
+    x = inp - target
+    return np.where(x < -1, -norm, np.where(x > 1, norm, norm * x)).astype(inp.dtype)
+
+
+def iou_counts(pred: np.ndarray, target: np.ndarray):
+    """util.lua:113-117: t = target > 0.5, et = pred > 0.5; per sample (#(t and et), #(t or et))."""
+    B = pred.shape[0]
+    t, e = target.reshape(B, -1) > 0.5, pred.reshape(B, -1) > 0.5
+    return np.stack([(t & e).sum(1), (t | e).sum(1)], 1).astype(np.uint64)
+
+
+# --------------------------------------------------------------------------------------------
 # the reference's own CUDA kernels recompiled for sm_100a (oracle/ref_cuda_shim.cu): the GPU incumbent.
 # Arguments are torch CUDA tensors; launches on the current stream, like the reference (...cu:706).
 # --------------------------------------------------------------------------------------------

@@ -324,3 +324,58 @@ def test_host_fused_modules_match_device_and_oracle(pinned, B):
     mo = vnn.CageWarpVolumetric(onlyGrid=True)
     gsrc2, gcage2 = mo.updateGradInput([t(src), t(cage)], t(go))
     assert float(gsrc2.abs().max()) == 0.0 and max_rel(gcage2.numpy(), ref_gcage) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# f4: forward + SmoothL1Criterion + its gradient + IoU counts + backward in one pass
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("oshape,cdims", [((16, 16, 16), (4, 4, 4)), ((7, 10, 37), (8, 8, 8)), ((9, 6, 70), (3, 5, 2))])
+@pytest.mark.parametrize("size_average", [True, False])
+def test_cage_warp_smooth_l1_step(oshape, cdims, size_average):
+    rng = np.random.default_rng(81 + oshape[2] + cdims[0])
+    B = 3
+    src = synth.volume("v2", B, *oshape, 1, rng)
+    src[1] *= 3.5                                           # |out - target| > 1 somewhere: the linear branch and the clamp
+    target = synth.volume("v2", B, *oshape, 1, rng)
+    cage = np.stack([synth.alignet_cage(1, max(cdims), rng)[0][:, :cdims[0], :cdims[1], :cdims[2]] for _ in range(B)]).astype(np.float32)
+    # the un-fused chain on the oracle
+    ref_out = cage_chain_oracle(src, cage, oshape)
+    ref_loss = oracle.smooth_l1_forward(ref_out, target, size_average)
+    go = oracle.smooth_l1_backward(ref_out, target, size_average)
+    _, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    ref_iou = oracle.iou_counts(ref_out, target)
+    for only_grid in (True, False):
+        m = vnn.CageWarpSmoothL1Volumetric(sizeAverage=size_average, onlyGrid=only_grid, keepOutput=True)
+        loss, (gsrc, gcage) = m.forwardBackward([dev(src), dev(cage)], dev(target))
+        assert bits_equal(host(m.output), ref_out)                                  # the forward value, bit for bit
+        assert abs(float(loss) - ref_loss) <= 1e-9 * max(1.0, abs(ref_loss))        # double accumulation, order only
+        assert np.array_equal(m.iouCounts.cpu().numpy().astype(np.uint64), ref_iou)  # exact integer counts
+        assert max_rel(host(gcage), ref_gcage) <= 1e-4, describe_mismatch(host(gcage), ref_gcage)
+        if only_grid:
+            assert float(gsrc.abs().max()) == 0.0
+        else:
+            assert max_rel(host(gsrc), ref_gsrc) <= 1e-4
+    # without keepOutput nothing but the gradients and the scalars leaves the kernel
+    m = vnn.CageWarpSmoothL1Volumetric(sizeAverage=size_average)
+    loss2, (_, gcage2) = m.forwardBackward([dev(src), dev(cage)], dev(target))
+    assert abs(float(loss2) - ref_loss) <= 1e-9 * max(1.0, abs(ref_loss)) and max_rel(host(gcage2), ref_gcage) <= 1e-4
+    ref_mean_iou = float(np.mean(ref_iou[:, 0].astype(np.float64) / ref_iou[:, 1].astype(np.float64)))
+    assert abs(float(m.iou()) - ref_mean_iou) <= 1e-12
+
+
+def test_smooth_l1_gradient_equals_chain_of_fused_modules():
+    """the step's gradCage against CageWarpVolumetric fed with the criterion's gradient computed by torch"""
+    rng = np.random.default_rng(91)
+    B, N = 2, 24
+    src, target = synth.volume("v2", B, N, N, N, 1, rng), synth.volume("v2", B, N, N, N, 1, rng)
+    cage = synth.alignet_cage(B, 6, rng).astype(np.float32)
+    ts, tc, tt = dev(src), dev(cage), dev(target)
+    cw = vnn.CageWarpVolumetric(onlyGrid=True)
+    out = cw.updateOutput([ts, tc]).clone().requires_grad_(True)
+    l = torch.nn.functional.smooth_l1_loss(out, tt)
+    l.backward()
+    _, gc_chain = cw.updateGradInput([ts, tc], out.grad)
+    step = vnn.CageWarpSmoothL1Volumetric()
+    loss, (_, gc) = step.forwardBackward([ts, tc], tt)
+    assert abs(float(loss) - float(l.detach())) <= 1e-6 * max(1.0, float(l.detach()))
+    assert max_rel(host(gc), host(gc_chain)) <= 1e-4
