@@ -169,20 +169,65 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
   zf = az, yf = ay, xf = ax;
 }
 
+// The same with the lane's eight cage corners kept in registers (compile with -DROW_CAGE_CACHE=1): a lane's x (hence
+// its cage column) is the same for every row of a one-trip kernel and the row's cage cell (z0, y0) changes only
+// every few rows, so the eight 16-byte shared-memory loads (4 wavefronts each: the L1/LSU pipe is what bounds the
+// cage kernels, 87 % busy in profiles/r01_row_kernels.md) are needed for about one row in nine.  Measured on a B200
+// and REJECTED (profiles/r01_fbench_history.txt): the 48 extra registers either spill (caps of 64 / 80 registers:
+// forward 270 / 247 us against 199 us) or halve the occupancy (cap 128: forward 192 us, backward 455 us against 366 us).
+#ifndef ROW_CAGE_CACHE
+#define ROW_CAGE_CACHE 0
+#endif
+struct CageCorners {
+  float vz[8], vy[8], vx[8];
+  int key;  // cell index of corner 0 the registers hold (-1: none)
+};
+__device__ __forceinline__ void cage_field_cached(const RowSmem &m, const RowArgs &a, int z, int y, int x, CageCorners &c,
+                                                  float &zf, float &yf, float &xf) {
+  const int cWp = a.cW + 1, cHWp = (a.cH + 1) * cWp;
+  const int base = (m.iz[z] * (a.cH + 1) + m.iy[y]) * cWp + m.ix[x];
+  if (base != c.key) {
+    const float4 *c0 = m.cg + base;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float4 v = c0[(k & 1) + ((k >> 1) & 1) * cWp + (k >> 2) * cHWp];
+      c.vz[k] = v.x, c.vy[k] = v.y, c.vx[k] = v.z;
+    }
+    c.key = base;
+  }
+  const float wx = m.tx[x], wy = m.ty[y], wz = m.tz[z];
+  const float wxs[2] = {wx, __fsub_rn(1.0f, wx)};
+  const float wys[2] = {wy, __fsub_rn(1.0f, wy)};
+  const float wzs[2] = {wz, __fsub_rn(1.0f, wz)};
+  float az = 0.f, ay = 0.f, ax = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float w = __fmul_rn(__fmul_rn(wxs[k & 1], wys[(k >> 1) & 1]), wzs[k >> 2]);
+    const float pz = __fmul_rn(w, c.vz[k]), py = __fmul_rn(w, c.vy[k]), px = __fmul_rn(w, c.vx[k]);
+    az = k ? __fadd_rn(az, pz) : pz;
+    ay = k ? __fadd_rn(ay, py) : py;
+    ax = k ? __fadd_rn(ax, px) : px;
+  }
+  zf = az, yf = ay, xf = ax;
+}
+
 template <int SRC, bool AOS4>
 struct RowCoords {
   // per-CTA state of the source
   float t[12];
   const float *gb;
+  CageCorners cc[(SRC == ROW_SRC_CAGE && ROW_CAGE_CACHE) ? 2 : 1];
   __device__ __forceinline__ void init(const RowArgs &a, int b) {
     if constexpr (SRC == ROW_SRC_AFFINE) {
 #pragma unroll
       for (int i = 0; i < 12; i++) t[i] = __ldg(a.T + (long long)b * 16 + i);
     }
     if constexpr (SRC == ROW_SRC_GRID) gb = opaque(a.s.grid + (long long)b * a.gB);
+    if constexpr (SRC == ROW_SRC_CAGE && ROW_CAGE_CACHE) cc[0].key = cc[1].key = -1;
   }
+  template <int V>  // V: slot of the trip (compile time: the corner registers of the two slots are distinct)
   __device__ __forceinline__ void get(const RowSmem &m, const RowArgs &a, int z, int y, int x, float &zf, float &yf,
-                                      float &xf) const {
+                                      float &xf) {
     if constexpr (SRC == ROW_SRC_GRID) {
       const float *g = gb + z * a.gD + y * a.gH + x * a.gW;
       if constexpr (AOS4) {
@@ -197,7 +242,10 @@ struct RowCoords {
       yf = affine_row(t, 1, zn, yn, xn);
       xf = affine_row(t, 2, zn, yn, xn);
     } else {
-      cage_field(m, a, z, y, x, zf, yf, xf);
+      if constexpr (ROW_CAGE_CACHE)
+        cage_field_cached(m, a, z, y, x, cc[V], zf, yf, xf);
+      else
+        cage_field(m, a, z, y, x, zf, yf, xf);
     }
   }
 };
@@ -348,11 +396,12 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_r
       row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
       VoxelSetup<float> su[2];
       int tier = 2;
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
+      {
         float zf, yf, xf;
-        src.get(m, a, sl[v].z, sl[v].y, sl[v].x, zf, yf, xf);
-        tier = min(tier, su[v].begin(zf, yf, xf, s));
+        src.template get<0>(m, a, sl[0].z, sl[0].y, sl[0].x, zf, yf, xf);
+        tier = min(tier, su[0].begin(zf, yf, xf, s));
+        src.template get<1>(m, a, sl[1].z, sl[1].y, sl[1].x, zf, yf, xf);
+        tier = min(tier, su[1].begin(zf, yf, xf, s));
       }
       float *o[2];
 #pragma unroll
@@ -476,11 +525,12 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_ro
       row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
       VoxelSetup<float> su[2];
       int tier = 2;
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
+      {
         float zf, yf, xf;
-        src.get(m, a, sl[v].z, sl[v].y, sl[v].x, zf, yf, xf);
-        tier = min(tier, su[v].begin(zf, yf, xf, s));
+        src.template get<0>(m, a, sl[0].z, sl[0].y, sl[0].x, zf, yf, xf);
+        tier = min(tier, su[0].begin(zf, yf, xf, s));
+        src.template get<1>(m, a, sl[1].z, sl[1].y, sl[1].x, zf, yf, xf);
+        tier = min(tier, su[1].begin(zf, yf, xf, s));
       }
       const float *gop[2];
 #pragma unroll

@@ -465,6 +465,15 @@ def _vol_view(t: torch.Tensor, layout: str) -> torch.Tensor:
     return t if layout == "BDHWC" else t.permute(0, 2, 3, 4, 1)
 
 
+def _reuse_or_new(cur, shape, like: torch.Tensor) -> torch.Tensor:
+    """``self.output:resize(...)`` of the Lua modules: keep the module's buffer when it already fits (for host
+    tensors this also keeps the pinned allocation)."""
+    if (isinstance(cur, torch.Tensor) and tuple(cur.shape) == tuple(shape) and cur.dtype == like.dtype
+            and cur.device == like.device and cur.is_contiguous()):
+        return cur
+    return torch.empty(shape, dtype=like.dtype, device=like.device, pin_memory=(not like.is_cuda and like.is_pinned()))
+
+
 class AffineSamplerVolumetric(Module):
     """``nn.ParallelTable():add(volume):add(nn.VolumetricGridGenerator(depth, height, width))`` followed by
     ``nn.BilinearSamplerVolumetric()`` -- the *projector* of stn3dtorch/test.lua:15-25 and the loader-side affine
@@ -494,7 +503,7 @@ class AffineSamplerVolumetric(Module):
         v = _vol_view(vol, self.layout)
         B, C = v.size(0), v.size(4)
         shape = (B, self.depth, self.height, self.width, C) if self.layout == "BDHWC" else (B, C, self.depth, self.height, self.width)
-        out = torch.empty(shape, dtype=vol.dtype, device=vol.device, pin_memory=(not vol.is_cuda and vol.is_pinned()))
+        out = _reuse_or_new(self.output, shape, vol)
         if vol.is_cuda:
             _require_device(vol.device.index)
             with torch.cuda.device(vol.device):
@@ -574,8 +583,7 @@ class CageWarpVolumetric(Module):
         v = _vol_view(vol, self.layout)
         B, C = v.size(0), v.size(4)
         d, h, w = self._out_dims(v)
-        out = torch.empty((B, d, h, w, C) if self.layout == "BDHWC" else (B, C, d, h, w), dtype=vol.dtype, device=vol.device,
-                          pin_memory=(not vol.is_cuda and vol.is_pinned()))
+        out = _reuse_or_new(self.output, (B, d, h, w, C) if self.layout == "BDHWC" else (B, C, d, h, w), vol)
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
         if vol.is_cuda:
             _require_device(vol.device.index)

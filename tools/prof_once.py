@@ -11,7 +11,7 @@ from alignet_b200 import nn as vnn
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=64); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--csz", type=int, default=8)
-ap.add_argument("--what", default="packed,row,affine,cage")
+ap.add_argument("--what", default="packed,row,affine,cage,step,cf")
 a = ap.parse_args()
 N, B, csz = a.size, a.batch, a.csz
 rng = np.random.default_rng(7)
@@ -35,5 +35,13 @@ if "cage" in what:
         m = vnn.CageWarpVolumetric(onlyGrid=og)
         if og: m.updateOutput([vol, cage])
         m.updateGradInput([vol, cage], go)
+if "step" in what:
+    tgt = rep(synth.volume("v2", nb, N, N, N, 1, rng))
+    vnn.CageWarpSmoothL1Volumetric().forwardBackward([vol, cage], tgt)
+if "cf" in what:
+    C, Bc = 4, max(1, B // 4)
+    volc = torch.randn((Bc, C, N, N, N), device="cuda"); goc = torch.randn((Bc, C, N, N, N), device="cuda")
+    gridc = rep(synth.grid("g2", nb, N, N, N, rng))[:Bc].permute(0, 4, 1, 2, 3).contiguous()
+    m = vnn.BilinearSamplerVolumetric(layout="BCDHW"); m.updateOutput([volc, gridc]); m.updateGradInput([volc, gridc], goc)
 torch.cuda.synchronize()
 print("ok")
