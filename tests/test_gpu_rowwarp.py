@@ -379,3 +379,28 @@ def test_smooth_l1_gradient_equals_chain_of_fused_modules():
     loss, (_, gc) = step.forwardBackward([ts, tc], tt)
     assert abs(float(loss) - float(l.detach())) <= 1e-6 * max(1.0, float(l.detach()))
     assert max_rel(host(gc), host(gc_chain)) <= 1e-4
+
+
+def test_batches_beyond_one_launch():
+    """more samples than gridDim.y allows (65535): the launchers walk the batch in chunks"""
+    rng = np.random.default_rng(95)
+    B = 66000
+    src = synth.volume("v1", B, 2, 2, 3, 1, rng)
+    go = synth.grad_output(B, 2, 2, 3, 1, rng)
+    cage = rng.uniform(-1.2, 1.2, (B, 3, 2, 2, 2)).astype(np.float32)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, (2, 2, 3), go)
+    m = vnn.CageWarpVolumetric()
+    assert bits_equal(host(m.updateOutput([dev(src), dev(cage)])), ref_out)
+    gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+    assert max_rel(host(gsrc), ref_gsrc) <= 1e-4 and max_rel(host(gcage), ref_gcage) <= 1e-4
+    T = random_affine(B, rng)
+    grid = host(vnn.VolumetricGridGenerator(2, 2, 3).updateOutput(dev(T)))
+    ma = vnn.AffineSamplerVolumetric(2, 2, 3)
+    assert bits_equal(host(ma.updateOutput([dev(src), dev(T)])), oracle.sampler_forward(src, grid))
+    _, gT = ma.updateGradInput([dev(src), dev(T)], dev(go))
+    assert max_rel(host(gT), oracle.gridgen_backward(oracle.sampler_backward(src, grid, go)[1])) <= 1e-5
+    mr = vnn.BilinearSamplerVolumetric(algo=_abi.ALGO_ROW)
+    assert bits_equal(host(mr.updateOutput([dev(src), dev(grid)])), oracle.sampler_forward(src, grid))
+    step = vnn.CageWarpSmoothL1Volumetric(keepOutput=True)
+    loss, _ = step.forwardBackward([dev(src), dev(cage)], dev(go))
+    assert abs(float(loss) - oracle.smooth_l1_forward(ref_out, go)) <= 1e-9

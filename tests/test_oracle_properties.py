@@ -109,3 +109,54 @@ def test_gridgen_restatement_known_answers():
     g = oracle.gridgen_forward(R[None], 4, 4, 4)
     assert np.allclose(g[0, ..., 1], oracle.gridgen_base(4, 4, 4, np.float64)[..., 2])
     assert np.allclose(g[0, ..., 2], -oracle.gridgen_base(4, 4, 4, np.float64)[..., 1])
+
+
+# ---------------------------------------------------------------------------------------------
+# the restatements behind the fused modules
+# ---------------------------------------------------------------------------------------------
+def test_smooth_l1_restatement_agrees_with_an_independent_implementation():
+    """THNN's SmoothL1Criterion is not vendored (parity unpinned); ATen's CPU smooth_l1_loss implements the same
+    published formula independently, so the two must agree (value in double, gradient in float)."""
+    import torch
+    rng = np.random.default_rng(21)
+    x = (3 * rng.standard_normal((2, 5, 6, 7, 1))).astype(np.float32)
+    t = (rng.standard_normal((2, 5, 6, 7, 1)) >= 0.5).astype(np.float32)
+    for size_average in (True, False):
+        # THNN subtracts in `real` (float) and accumulates in double: feed the float difference against zero
+        tx = torch.from_numpy((x - t).astype(np.float64)).requires_grad_(True)
+        loss = torch.nn.functional.smooth_l1_loss(tx, torch.zeros_like(tx), reduction="mean" if size_average else "sum")
+        loss.backward()
+        assert abs(oracle.smooth_l1_forward(x, t, size_average) - float(loss.detach())) <= 1e-12 * max(1.0, float(loss.detach()))
+        g = oracle.smooth_l1_backward(x, t, size_average)
+        assert g.dtype == np.float32
+        assert np.max(np.abs(g - tx.grad.numpy())) <= 2e-7 * np.max(np.abs(tx.grad.numpy()))
+    # the three branches of the gradient: -norm, norm * x, +norm
+    g = oracle.smooth_l1_backward(np.array([-3.0, 0.25, 3.0], np.float32), np.zeros(3, np.float32), False)
+    assert list(g) == [-1.0, 0.25, 1.0]
+
+
+def test_iou_counts_follow_util_lua():
+    """util.lua:113-117: thresholds at 0.5 (strict), per-sample intersection and union"""
+    pred = np.array([[0.6, 0.5, 0.7, 0.1], [0.0, 0.0, 0.0, 0.0]], np.float32).reshape(2, 1, 1, 4, 1)
+    tgt = np.array([[1.0, 1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]], np.float32).reshape(2, 1, 1, 4, 1)
+    c = oracle.iou_counts(pred, tgt)
+    assert c.tolist() == [[1, 3], [0, 1]]
+
+
+def test_alignet_initial_cage_warps_to_identity():
+    """models/alignet_2d.lua:77-80,118-119 + Cumsum.lua:17-19: weight 0 / bias del gives the cage linspace(-1, 1, csz),
+    whose trilinear up-sample at the identity field is the identity field again: the chain reproduces the source."""
+    csz, N = 6, 12
+    delta = 2.0 / (csz - 1)
+    d = np.full((1, 3, csz, csz, csz), delta, np.float32)
+    cage = oracle.cumsum_forward(d) + np.float32(-1 - delta)
+    ax = np.linspace(-1, 1, csz)
+    assert np.max(np.abs(cage[0, 0] - ax[:, None, None])) < 1e-6 and np.max(np.abs(cage[0, 2] - ax[None, None, :])) < 1e-6
+    base = oracle.gridgen_base(N, N, N)[None]
+    cage_vol = np.ones((1, csz, csz, csz, 4), np.float32)
+    cage_vol[..., :3] = np.moveaxis(cage, 1, -1)
+    field = oracle.sampler_forward(cage_vol, np.ascontiguousarray(base))
+    assert np.max(np.abs(field[..., :3] - base[..., :3])) < 1e-6
+    rng = np.random.default_rng(4)
+    src = synth.volume("v1", 1, N, N, N, 1, rng)
+    assert np.max(np.abs(oracle.sampler_forward(src, field) - src)) < 2e-5
