@@ -43,13 +43,14 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
   for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
     const size_t sb = (size_t)b * n;  // first voxel of the sample in the packed batch
     const real *vb = opaque(a.vol + (size_t)b * a.vs32);
-    const real *gb = opaque(a.grid + sb * G);
+    constexpr int GC = G % 10, GS = G >= 10 ? 1 : G;  // components; element stride of a voxel (planar grid: 1)
+    const real *gb = opaque(a.grid + sb * GC);
     real *ob = opaque(a.out + sb * C);
     real zf[VPT], yf[VPT], xf[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
       const unsigned j = min(j0 + v * kThreads, n - 1);
-      ld_grid<real, G>(gb + (size_t)j * G, zf[v], yf[v], xf[v]);
+      ld_grid<real, G>(gb + (size_t)j * GS, zf[v], yf[v], xf[v], n);
     }
     if constexpr (CT > 0) {
       // one vote for all VPT voxels of the thread: inside the fast block the bodies are straight-line
@@ -107,14 +108,15 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
     const size_t sb = (size_t)b * n;
     const real *vb = opaque(a.vol + (size_t)b * a.vs32);
     real *gvb = const_cast<real *>(vb) + gv_delta;
-    const real *gb = opaque(a.grid + sb * G);
-    real *ggb = opaque(a.ggrid + sb * G);
+    constexpr int GC = G % 10, GS = G >= 10 ? 1 : G;
+    const real *gb = opaque(a.grid + sb * GC);
+    real *ggb = opaque(a.ggrid + sb * GC);
     const real *gob = opaque(a.gout + sb * C);
     real zf[VPT], yf[VPT], xf[VPT], go[VPT][CR];
 #pragma unroll
     for (int v = 0; v < VPT; v++) {
       const size_t j = min(j0 + v * kThreads, n - 1);
-      ld_grid<real, G>(gb + j * G, zf[v], yf[v], xf[v]);
+      ld_grid<real, G>(gb + j * GS, zf[v], yf[v], xf[v], n);
       if constexpr (CT > 0) ld_channels_stream<real, CR>(gob + j * C, go[v]);
     }
     if constexpr (CT > 0) {
@@ -130,10 +132,10 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
           const unsigned j = j0 + v * kThreads;
           if (a.quad)
             voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1, true>(a, s[v], vb, gv_delta, sD, sH, go[v],
-                                                                         ggb + (size_t)j * G, j < n);
+                                                                         ggb + (size_t)j * GS, j < n);
           else
             voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1, false>(a, s[v], vb, gv_delta, sD, sH, go[v],
-                                                                          ggb + (size_t)j * G, j < n);
+                                                                          ggb + (size_t)j * GS, j < n);
         }
       } else if (__all_sync(0xffffffffu, tier >= 1)) {
 #pragma unroll
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
         for (int v = 0; v < VPT; v++) {
           const unsigned j = j0 + v * kThreads;
           voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 2>(a, s[v], vb, gv_delta, sD, sH, go[v],
-                                                                 ggb + (size_t)j * G, j < n);
+                                                                 ggb + (size_t)j * GS, j < n);
         }
       } else {
 #pragma unroll
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
           const unsigned j = j0 + v * kThreads;
           s[v].finish_exact(a);
           voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 0>(a, s[v], vb, gv_delta, sD, sH, go[v],
-                                                                 ggb + (size_t)j * G, j < n);
+                                                                 ggb + (size_t)j * GS, j < n);
         }
       }
     } else {
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
         s.init(zf[v], yf[v], xf[v], a);
         if (j < n)
           voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + (size_t)j * C,
-                                                                  ggb + (size_t)j * G);
+                                                                  ggb + (size_t)j * GS);
       }
     }
   }
@@ -485,7 +487,7 @@ int launch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   switch (vpt) {
     case 4: k_sampler_fwd_packed<float, CT, G, 4><<<dim3(blocks_x(4), by), block, 0, st>>>(a); break;
     case 2:
-      if constexpr (CT > 0) {
+      if constexpr (CT > 0 && G < 10) {
         if (!a.no_pair) {
           k_sampler_fwd_pair<CT, G><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
           break;
@@ -527,7 +529,7 @@ int launch_bwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 2:
-      if constexpr (CT > 0) {
+      if constexpr (CT > 0 && G < 10) {
         if (!a.no_pair) {
           k_sampler_bwd_pair<CT, G, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
           break;
@@ -596,6 +598,24 @@ bool packed_ok(int G, const volstn_tensor5 *vol, std::initializer_list<const vol
   return true;
 }
 
+// single-channel contiguous volume (channels-last and channel-first coincide) with a PLANAR contiguous grid, i.e. the
+// `B x D x H x W x G` view of a contiguous `B x G x D x H x W` tensor: the packed kernels with three coalesced
+// component loads instead of one 128-bit load
+bool planar_grid(const volstn_tensor5 *g) {
+  const int64_t n = g->size[1] * g->size[2] * g->size[3];
+  return g->stride[4] == n && g->stride[3] == 1 && g->stride[2] == g->size[3] && g->stride[1] == g->size[2] * g->size[3] &&
+         g->stride[0] == g->size[4] * n && n < 0x7fffffffLL && aligned(g->data, 4);
+}
+bool planar_ok(const volstn_tensor5 *vol, const volstn_tensor5 *grid, const volstn_tensor5 *gradGrid,
+               std::initializer_list<const volstn_tensor5 *> packed) {
+  if (vol->size[4] != 1 || !is_contiguous(vol) || !planar_grid(grid)) return false;
+  if (gradGrid && !planar_grid(gradGrid)) return false;
+  if (vol->size[1] * vol->size[2] * vol->size[3] >= 0x7fffffffLL) return false;
+  for (const volstn_tensor5 *t : packed)
+    if (t && !is_contiguous(t)) return false;
+  return true;
+}
+
 }  // namespace
 
 int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
@@ -618,6 +638,8 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
       const int vpt = pick_vpt(flags, a.C, a.n);
       return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
     }
+    if (!force_row && planar_ok(vol, grid, nullptr, {out}))  // channel-first field, single-channel volume
+      return G == 4 ? launch_fwd_packed<1, 14>(a, 2, st) : launch_fwd_packed<1, 13>(a, 2, st);
     // strided or planar tensors (e.g. permuted views of B x C x D x H x W tensors): the row kernels
     if ((rc = row_sampler_forward(G, vol, grid, out, flags, st)) != -1) return rc;
     return launch_fwd_generic<float>(a, G, st);
@@ -684,6 +706,11 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       if (vpt != 1 && vpt != 2) vpt = 2;
       return G == 4 ? dispatch_bwd_packed<4>(a, og, ov, vpt, st)
                     : dispatch_bwd_packed<3>(a, og, ov, vpt, st);
+    }
+    if (!force_row && planar_ok(vol, grid, ov ? nullptr : gradGrid, {gradOut, og ? nullptr : gradVol})) {
+      if (og) return G == 4 ? launch_bwd_packed<1, 14, true, false>(a, 2, st) : launch_bwd_packed<1, 13, true, false>(a, 2, st);
+      if (ov) return G == 4 ? launch_bwd_packed<1, 14, false, true>(a, 2, st) : launch_bwd_packed<1, 13, false, true>(a, 2, st);
+      return G == 4 ? launch_bwd_packed<1, 14, false, false>(a, 2, st) : launch_bwd_packed<1, 13, false, false>(a, 2, st);
     }
     if ((rc = row_sampler_backward(G, vol, grid, gradVol, gradGrid, gradOut, og, ov, flags, st)) != -1) return rc;
     return launch_bwd_generic<float>(a, G, og, ov, st);

@@ -255,10 +255,15 @@ __device__ __forceinline__ void red_channels(real *p, const real (&v)[CT]) {
   }
 }
 
-// grid element (z, y, x): one 128-bit streaming load for float G = 4
+// grid element (z, y, x): one 128-bit streaming load for float G = 4.
+// G >= 10 (packed float kernels only) = PLANAR grid with G % 10 components: the `B x G x D x H x W` tensor a
+// convolutional network emits, handed over as its permuted view; `plane` = voxels per sample, `g`
+// points at component 0 of the voxel and the three loads of a warp are three coalesced 128-byte rows.
 template <typename real, int G>
-__device__ __forceinline__ void ld_grid(const real *g, real &zf, real &yf, real &xf) {
-  if constexpr (sizeof(real) == 4 && G == 4) {
+__device__ __forceinline__ void ld_grid(const real *g, real &zf, real &yf, real &xf, unsigned plane = 0) {
+  if constexpr (G >= 10) {
+    zf = ld_stream_f1(g), yf = ld_stream_f1(g + plane), xf = ld_stream_f1(g + 2 * (size_t)plane);
+  } else if constexpr (sizeof(real) == 4 && G == 4) {
     const float4 t = ld_stream_f4(reinterpret_cast<const float4 *>(g));
     zf = t.x; yf = t.y; xf = t.z;
   } else if constexpr (sizeof(real) == 4) {
@@ -269,8 +274,11 @@ __device__ __forceinline__ void ld_grid(const real *g, real &zf, real &yf, real 
 }
 
 template <typename real, int G>
-__device__ __forceinline__ void st_grad_grid(real *g, real gz, real gy, real gx) {
-  if constexpr (sizeof(real) == 4 && G == 4) {
+__device__ __forceinline__ void st_grad_grid(real *g, real gz, real gy, real gx, unsigned plane = 0) {
+  if constexpr (G >= 10) {
+    st_stream_f1(g, gz), st_stream_f1(g + plane, gy), st_stream_f1(g + 2 * (size_t)plane, gx);
+    if constexpr (G % 10 == 4) st_stream_f1(g + 3 * (size_t)plane, real(0));  // ...c:822
+  } else if constexpr (sizeof(real) == 4 && G == 4) {
     st_stream_f4(reinterpret_cast<float4 *>(g), make_float4(gz, gy, gx, 0.0f));
   } else {
     g[0] = gz; g[1] = gy; g[2] = gx;
@@ -333,7 +341,7 @@ __device__ __forceinline__ void voxel_forward_ct(const VoxelSetup<real> &s, cons
   real acc[CT];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    const int k = (G == 4) ? order_xyz(j) : order_zxy(j);  // ...c:566-573 / ...c:149-156
+    const int k = (G % 10 == 4) ? order_xyz(j) : order_zxy(j);  // ...c:566-573 / ...c:149-156
 #pragma unroll
     for (int t = 0; t < CT; t++) {
       const real term = E::mul(cw[k], v[k][t]);
@@ -442,7 +450,7 @@ __device__ __forceinline__ void voxel_backward_ct(const SamplerArgs<real> &a, co
   if constexpr (!ONLY_VOL) {
     real gz, gy, gx;
     grad_grid_from_dots<real>(dot, s, a, gz, gy, gx);
-    if (valid) st_grad_grid<real, G>(ggp, gz, gy, gx);
+    if (valid) st_grad_grid<real, G>(ggp, gz, gy, gx, a.n32);
   }
 }
 

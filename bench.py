@@ -672,6 +672,26 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         "speedup_fwd": c_f / f_f, "speedup_bwd": c_b / f_b, "speedup_step": (c_f + c_b) / (f_f + f_b)}
     del volc, goc, gridc
 
+    # the ALIGNet case: single-channel volume (layouts coincide), channel-first FIELD as a conv net emits it -- the packed
+    # kernels with planar component loads
+    gridn = rep(synth.grid("g1", nb, N, N, N, rng))
+    grid1 = gridn.permute(0, 4, 1, 2, 3).contiguous()
+    vol1, go1 = vol.permute(0, 4, 1, 2, 3).contiguous(), go.permute(0, 4, 1, 2, 3).contiguous()
+    n_f = timed(lambda: clm.updateOutput([vol, gridn]))
+    n_b = timed(lambda: clm.updateGradInput([vol, gridn], go))
+    c_f = timed(lambda: cf(clm.updateOutput([cl(vol1), cl(grid1)])))
+    c_b = timed(lambda: [cf(g) for g in clm.updateGradInput([cl(vol1), cl(grid1)], cl(go1))], k=3)
+    f_f = timed(lambda: cfm.updateOutput([vol1, grid1]))
+    f_b = timed(lambda: cfm.updateGradInput([vol1, grid1], go1))
+    res["channel_first_c1"] = {
+        "what": f"B x 1 x D x H x W volume, B x 4 x D x H x W field (identity field g1), batch {B}: native-layout tensors / nn.Transpose copies + sampler / in place",
+        "native_layout": {"fwd_ms": n_f, "bwd_ms": n_b},
+        "chain": {"fwd_ms": c_f, "bwd_ms": c_b, "voxels_per_s": V / ((c_f + c_b) * 1e-3)},
+        "in_place": {"fwd_ms": f_f, "bwd_ms": f_b, "voxels_per_s": V / ((f_f + f_b) * 1e-3),
+                     "step_frac_of_hbm_peak": (fwd_bytes(1) + bwd_bytes(1)) * V / ((f_f + f_b) * 1e-3) / 1e9 / peak},
+        "speedup_step": (c_f + c_b) / (f_f + f_b)}
+    del gridn, grid1, vol1, go1
+
     # ---- BASELINE.json config 2 with the fused module: Cumsum -> +beta -> CageWarp, forward and backward ---------
     Np, Bp = 32, 32
     delta = 2.0 / (csz - 1)

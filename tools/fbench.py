@@ -111,6 +111,20 @@ def main():
         report("cage FUSED bwd (gradSource + gradCage)", b_ff, 12 * V, f"x{(b_wf + b_up) / b_ff:.2f}")
         del field, field_i, gfield
 
+    if "cf1" in what:
+        # channel-first field (B x 4 x D x H x W, what a conv net emits) with a single-channel volume: the packed kernels
+        # with planar component loads against the native layout and against the row kernels on the same views
+        for gk in ("g1", "g2"):
+            grid = rep(synth.grid(gk, nb, N, N, N, rng))
+            gridp = grid.permute(0, 4, 1, 2, 3).contiguous()
+            volp = vol.permute(0, 4, 1, 2, 3).contiguous(); gop = go.permute(0, 4, 1, 2, 3).contiguous()
+            for nm, m, args, garg in (("native layout (packed)", vnn.BilinearSamplerVolumetric(), [vol, grid], go),
+                                      ("channel-first, packed+planar grid", vnn.BilinearSamplerVolumetric(layout="BCDHW"), [volp, gridp], gop),
+                                      ("channel-first, row kernels", vnn.BilinearSamplerVolumetric(layout="BCDHW", algo=_abi.ALGO_ROW), [volp, gridp], gop)):
+                f = timed(lambda: m.updateOutput(args)); b = timed(lambda: m.updateGradInput(args, garg))
+                report(f"cf1 {gk} {nm} fwd", f, 24 * V); report(f"cf1 {gk} {nm} bwd+memset", b, 44 * V)
+            del grid, gridp
+
     if "cf" in what:
         C = a.channels
         Bc = max(1, B // C)
