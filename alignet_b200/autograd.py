@@ -57,3 +57,55 @@ def bilinear_sampler_volumetric(vol: torch.Tensor, grid: torch.Tensor, module: v
 def cumsum(x: torch.Tensor, module: vnn.Cumsum = None):
     """nn.Cumsum on B x N x d1..dN; differentiable."""
     return _Cumsum.apply(x, module or vnn.Cumsum())
+
+
+class _CageWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol, cage, module):
+        ctx.module = module
+        ctx.save_for_backward(vol, cage)
+        return module.updateOutput([vol, cage]).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        vol, cage = ctx.saved_tensors
+        need_vol, need_cage = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        m = ctx.module
+        saved = m.onlyGrid
+        m.onlyGrid = not need_vol   # the source is data in ALIGNet training (models/alignet_2d.lua:23-24)
+        try:
+            gv, gc = m.updateGradInput([vol, cage], grad_out.contiguous())
+        finally:
+            m.onlyGrid = saved
+        return (gv.clone() if need_vol else None), (gc.clone() if need_cage else None), None
+
+
+class _CageWarpSmoothL1(torch.autograd.Function):
+    """loss = SmoothL1(CageWarp(vol, cage), target): forward AND backward happen in the forward call (one kernel);
+    backward only scales the stored cage gradient by the incoming scalar."""
+
+    @staticmethod
+    def forward(ctx, vol, cage, target, module):
+        loss, (gv, gc) = module.forwardBackward([vol, cage], target)
+        ctx.save_for_backward(gc, gv)
+        ctx.only_grid = module.onlyGrid
+        return loss.to(vol.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        gc, gv = ctx.saved_tensors
+        g = grad_loss.to(gc.dtype)
+        need_vol = ctx.needs_input_grad[0] and not ctx.only_grid
+        return (gv * g if need_vol else None), gc * g, None, None
+
+
+def cage_warp_volumetric(vol: torch.Tensor, cage: torch.Tensor, module: vnn.CageWarpVolumetric = None):
+    """out = sample(vol, up-sample(cage B x 3 x cD x cH x cW)); differentiable in both arguments (one kernel each way)."""
+    return _CageWarp.apply(vol, cage, module or vnn.CageWarpVolumetric())
+
+
+def cage_warp_smooth_l1(vol: torch.Tensor, cage: torch.Tensor, target: torch.Tensor,
+                        module: vnn.CageWarpSmoothL1Volumetric = None):
+    """SmoothL1Criterion(cage_warp(vol, cage), target) as a scalar, differentiable in the cage (and in the volume when the
+    module was built with onlyGrid=False); the warp, the criterion and both backward passes are ONE kernel launch."""
+    return _CageWarpSmoothL1.apply(vol, cage, target, module or vnn.CageWarpSmoothL1Volumetric())

@@ -55,6 +55,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--global-batch", type=int, default=64); ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--fused", type=int, default=0, help="0: un-fused modules; 1: CageWarpVolumetric + torch criterion; 2: the one-kernel step")
     a = ap.parse_args()
     out_fd = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)                   # stdout = the JSON line only
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -74,6 +75,7 @@ def main():
     gen = vnn.VolumetricGridGenerator(N, N, N)
     field_i = gen.updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))         # constant, like fieldI (dataset_2d.lua:128)
     up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
+    fwarp, fstep = vnn.CageWarpVolumetric(), vnn.CageWarpSmoothL1Volumetric()
     params = [p for p in net.parameters()]
     crit = tnn.SmoothL1Loss()
     ones = torch.ones((B, csz, csz, csz, 1), device="cuda")
@@ -83,10 +85,17 @@ def main():
         cage = net(pair)                                                            # B x 3 x csz^3
         cage_vol = torch.cat([cage.permute(0, 2, 3, 4, 1), ones], dim=-1).contiguous()   # channels-last, 4th coord
         if timers: timers[0].record()
-        field = vag.bilinear_sampler_volumetric(cage_vol, field_i, up)              # cage up-sample -> B x N^3 x 4
-        est = vag.bilinear_sampler_volumetric(src, field, warp)                     # source warp
-        if timers: timers[1].record()
-        loss = crit(est, tgt)
+        if a.fused == 2:                                                            # warp + criterion + both backwards: one kernel
+            loss = vag.cage_warp_smooth_l1(src, cage.contiguous(), tgt, fstep)
+            if timers: timers[1].record()
+        else:
+            if a.fused == 1:
+                est = vag.cage_warp_volumetric(src, cage.contiguous(), fwarp)       # cage up-sample + source warp: one kernel
+            else:
+                field = vag.bilinear_sampler_volumetric(cage_vol, field_i, up)      # cage up-sample -> B x N^3 x 4
+                est = vag.bilinear_sampler_volumetric(src, field, warp)             # source warp
+            if timers: timers[1].record()
+            loss = crit(est, tgt)
         loss.backward()
         if world > 1:                                                               # the one collective of the step
             flat = torch.cat([p.grad.reshape(-1) for p in params])
@@ -120,7 +129,7 @@ def main():
         print(json.dumps({"config": "ALIGNet-3D training step (BASELINE.json config 3)", "size": N, "global_batch": a.global_batch,
                           "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "samples_per_s": a.global_batch / (ms * 1e-3),
                           "voxels_per_s": a.global_batch * N ** 3 / (ms * 1e-3), "loss": float(loss.detach()),
-                          "warp_forward_ms": warp_fwd_ms, "volstn_kernels_per_step": int(launches),
+                          "warp_forward_ms": warp_fwd_ms, "fused": a.fused, "volstn_kernels_per_step": int(launches),
                           "allreduce_floats": nparam if world > 1 else 0, "scaling": "strong",
                           "note": "CNN = plain PyTorch (3-D lift of models/alignet_2d.lua); Cumsum, grid generator and both samplers = this repo's kernels; one NCCL all-reduce of the CNN gradients per step"}),
               file=out_fd, flush=True)
