@@ -410,6 +410,7 @@ void fill_fast(SamplerArgs<real> &a) {
   a.border_ok = 0;
   a.no_pair = 1;
   a.quad = 0;
+  a.tile_agg = 0;
   a.one = 1.0f;
   if constexpr (sizeof(real) == 4) {
     if (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) {
@@ -700,7 +701,15 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     if (!force_row && packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
       a.quad = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_QUAD && !og && a.C == 1 && a.iW % 4 == 0 &&
                 reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0) ? 1 : 0;
+      a.tile_agg = a.n >= 128LL * a.iD * a.iH * a.iW;
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
+        return launch_bwd_tile(a, G, ov, st);
+      // Automatic choice: a volume much smaller than the output (ALIGNet's cage up-sample: 16.8 M voxels scatter
+      // into 4^3 .. 12^3 cells per sample, models/alignet_2d.lua:136-147) serialises the direct kernel's global
+      // reductions on a handful of addresses -- 22.5 ms at 4^3, 3.0 ms at 8^3, 1.15 ms at 12^3 for 64^3 x 64 -- while the
+      // privatised kernel folds a brick's 2048 contributions into a few cells first (and warp-aggregates its shared
+      // atomics, sampler_tile.cu): 0.77 / 1.07 / 1.05 ms (tools/upbench.py, profiles/r01_upsample_backward.txt).
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_AUTO && !og && tile_supported(a) && a.tile_agg)
         return launch_bwd_tile(a, G, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
       if (vpt != 1 && vpt != 2) vpt = 2;
