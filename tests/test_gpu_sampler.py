@@ -358,3 +358,26 @@ def test_tiers_are_bit_identical(C):
                     gv, gg = m.updateGradInput([dev(vol), dev(grid)], dev(go))
                     assert bits_equal(gg.cpu().numpy(), rgg), (name, vpt, hex(dbg), describe_mismatch(gg.cpu().numpy(), rgg))
                     assert_gradvol_close(gv.cpu().numpy(), rgv, (name, vpt, hex(dbg)))
+
+
+@pytest.mark.parametrize("C", [1, 2, 4])
+@pytest.mark.parametrize("gk", ["g1", "g2", "g3", "g4"])
+def test_small_volume_under_large_output_uses_privatised_backward(C, gk):
+    """ALIGNet's cage up-sample in the reference's own module graph (models/alignet_2d.lua:136-147): a csz^3 volume
+    sampled at a full-resolution field.  The automatic algorithm is the privatised, warp-aggregated kernel there
+    (output voxels >= 128 x volume cells); same contract as everywhere: gradGrid bit-exact, gradVol within 1e-4."""
+    rng = np.random.default_rng(300 + C + ord(gk[1]))
+    B, ishape, oshape = 3, (3, 5, 4), (20, 18, 40)
+    vol = synth.volume("v1", B, *ishape, C, rng)
+    grid = synth.grid(gk, B, *oshape, rng, csz=4)
+    go = synth.grad_output(B, *oshape, C, rng)
+    ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go)
+    for kw in (dict(), dict(onlyVolume=True), dict(algo=_abi.ALGO_DIRECT)):
+        gv, gg = cuda_backward(vol, grid, go, **kw)
+        assert_gradvol_close(gv, ref_gv, (kw, max_rel(gv, ref_gv)))
+        if "onlyVolume" not in kw:
+            assert bits_equal(gg, ref_gg), (kw, describe_mismatch(gg, ref_gg))
+    # a constant gradOut puts every lane of a warp on the same few cells with equal signs: the aggregation's worst case
+    ones = np.ones_like(go)
+    gv, _ = cuda_backward(vol, grid, ones)
+    assert_gradvol_close(gv, oracle.sampler_backward(vol, grid, ones)[0])
