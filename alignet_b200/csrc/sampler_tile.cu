@@ -163,14 +163,19 @@ __global__ void __launch_bounds__(kTileThreads, 5)
     // (the contributions are integers) and one lane per cell issues the atomic.  The groups of a warp execute their
     // REDUX one after the other (different member masks), so this pays only for very few, large groups: taken when
     // the launch is in the small-volume regime (a.tile_agg, set by the host) AND the warp holds at most three
-    // distinct cells (warp-uniform).  Measured at 64^3 x 64: 4^3 cage 1718 -> 771 us, 8^3 1308 -> 1066 us; with a
-    // threshold of eight cells the 12^3 cage lost 20 %; sheared fields on large volumes never enter (no MATCH).
-    unsigned grp = 0;
-    bool lead = false, aggregate = false;
+    // distinct cells (warp-uniform).  With a threshold of eight cells the 12^3 cage lost 20 %; sheared fields on
+    // large volumes never enter (no MATCH).
+    // (REDUX with a partial member mask is emulated by a loop -- 940 instructions per voxel-warp -- so each of the
+    // at most three groups is reduced with a full-mask REDUX over `lane in group ? q : 0`.)
+    bool lead = false;
+    int gid = 0, ngroups = 0;  // ngroups = 0: per-lane atomics
     if (a.tile_agg) {
-      grp = __match_any_sync(0xffffffffu, t0);
-      lead = (int)(threadIdx.x & 31) == __ffs(grp) - 1;
-      aggregate = __popc(__ballot_sync(0xffffffffu, lead)) <= 3;
+      const unsigned grp = __match_any_sync(0xffffffffu, t0);
+      const int leader = __ffs(grp) - 1;
+      lead = (int)(threadIdx.x & 31) == leader;
+      const unsigned leaders = __ballot_sync(0xffffffffu, lead);
+      gid = __popc(leaders & ((1u << leader) - 1u));
+      ngroups = __popc(leaders) <= 3 ? __popc(leaders) : 0;
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -181,9 +186,14 @@ __global__ void __launch_bounds__(kTileThreads, 5)
         // round(c * scale) without a conversion instruction: |c * scale| < 2^21, so adding 1.5 * 2^23
         // leaves the integer in the mantissa
         const int q = __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000;
-        if (aggregate) {
-          const int sum = __reduce_add_sync(grp, q);
-          if (lead) atomicAdd(cell + t, sum);
+        if (ngroups) {
+#pragma unroll
+          for (int g = 0; g < 3; g++) {
+            if (g < ngroups) {  // warp-uniform
+              const int sum = __reduce_add_sync(0xffffffffu, gid == g ? q : 0);
+              if (lead && gid == g) atomicAdd(cell + t, sum);
+            }
+          }
         } else {
           atomicAdd(cell + t, q);
         }
