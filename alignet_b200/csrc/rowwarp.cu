@@ -366,9 +366,13 @@ __device__ __forceinline__ void row_advance(int &z, int &y, int step, int oH) {
 #ifndef ROW_MIN_CTAS
 #define ROW_MIN_CTAS 0
 #endif
-constexpr int row_min_ctas(int src, bool bwd, bool c1) {
+#ifndef ROW_MIN_CTAS_HEAVY
+#define ROW_MIN_CTAS_HEAVY 3
+#endif
+constexpr int row_min_ctas(int src, bool bwd, bool c1, bool heavy = false) {
   if (ROW_MIN_CTAS) return ROW_MIN_CTAS;
   if (!c1) return 3;
+  if (heavy) return ROW_MIN_CTAS_HEAVY;  // cage backward WITH the gradVol scatter: 552 us at 3, 618 us at 4, 577 us at 2
   return (src == ROW_SRC_GRID && !bwd) ? 5 : 4;
 }
 
@@ -485,7 +489,8 @@ struct CageAcc {
 };
 
 template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false>
-__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1)) k_row_bwd(const RowArgs a) {
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, SRC == ROW_SRC_CAGE && !OG))
+    k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];
   const SamplerArgs<float> &s = a.s;
