@@ -372,7 +372,9 @@ __device__ __forceinline__ void row_advance(int &z, int &y, int step, int oH) {
 constexpr int row_min_ctas(int src, bool bwd, bool c1, bool heavy = false) {
   if (ROW_MIN_CTAS) return ROW_MIN_CTAS;
   if (!c1) return 3;
-  if (heavy) return ROW_MIN_CTAS_HEAVY;  // cage backward WITH the gradVol scatter: 552 us at 3, 618 us at 4, 577 us at 2
+  // cage backward WITH the gradVol scatter (552 us at 3, 618 us at 4, 577 us at 2) and the affine backward with its
+  // twelve gradT accumulators (277 us at 3, 287 us at 4, 306 us at 2)
+  if (heavy) return ROW_MIN_CTAS_HEAVY;
   return (src == ROW_SRC_GRID && !bwd) ? 5 : 4;
 }
 
@@ -489,7 +491,7 @@ struct CageAcc {
 };
 
 template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false>
-__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, SRC == ROW_SRC_CAGE && !OG))
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC == ROW_SRC_CAGE && !OG) || SRC == ROW_SRC_AFFINE))
     k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];

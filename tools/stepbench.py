@@ -1,3 +1,5 @@
+"""tools/stepbench.py -- the cage warp backward and the one-kernel training step, with and without the gradVol scatter
+(used to choose the register caps of rowwarp.cu::row_min_ctas)."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
