@@ -404,3 +404,61 @@ def test_batches_beyond_one_launch():
     step = vnn.CageWarpSmoothL1Volumetric(keepOutput=True)
     loss, _ = step.forwardBackward([dev(src), dev(cage)], dev(go))
     assert abs(float(loss) - oracle.smooth_l1_forward(ref_out, go)) <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json sizes: the fused modules against the chain of un-fused CUDA modules (each parity-tested against the
+# oracle on its own) plus size-independent properties, and one sample against the oracle chain
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,B,csz", [(32, 32, 8), (64, 16, 8), (64, 8, 4)])
+def test_fused_modules_at_full_size(N, B, csz):
+    rng = np.random.default_rng(N + B + csz)
+    src_np = synth.volume("v2", B, N, N, N, 1, rng)
+    tgt_np = synth.volume("v2", B, N, N, N, 1, rng)
+    cage_np = synth.alignet_cage(B, csz, rng).astype(np.float32)
+    src, tgt, cage = dev(src_np), dev(tgt_np), dev(cage_np)
+    go = dev(synth.grad_output(B, N, N, N, 1, rng))
+    # the un-fused chain on the GPU
+    field_i = vnn.VolumetricGridGenerator(N, N, N).updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))
+    cage_vol = torch.ones((B, csz, csz, csz, 4), device="cuda")
+    cage_vol[..., :3] = cage.permute(0, 2, 3, 4, 1)
+    up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
+    field = up.updateOutput([cage_vol, field_i]).clone()
+    ref_out = warp.updateOutput([src, field]).clone()
+    ref_gsrc, gfield = [t.clone() for t in warp.updateGradInput([src, field], go)]
+    ref_gcage = up.updateGradInput([cage_vol, field_i], gfield)[0][..., :3].permute(0, 4, 1, 2, 3).contiguous()
+    # (1) the fused warp: same bits forward, same gradients within the accumulation tolerance
+    m = vnn.CageWarpVolumetric()
+    out = m.updateOutput([src, cage]).clone()
+    assert torch.equal(out, ref_out)
+    gsrc, gcage = m.updateGradInput([src, cage], go)
+    assert float((gcage - ref_gcage).abs().max()) <= 1e-4 * float(ref_gcage.abs().max())
+    assert float((gsrc - ref_gsrc).abs().max()) <= 1e-4 * float(ref_gsrc.abs().max())
+    # (2) adjointness in the source: <warp(src), go> == <src, gradSource>
+    lhs, rhs = float((out.double() * go.double()).sum()), float((gsrc.double() * src.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+    # (3) the identity cage reproduces the source (ALIGNet at initialisation)
+    ax = torch.linspace(-1, 1, csz, device="cuda")
+    idc = torch.stack([ax.view(-1, 1, 1).expand(csz, csz, csz), ax.view(1, -1, 1).expand(csz, csz, csz),
+                       ax.view(1, 1, -1).expand(csz, csz, csz)]).unsqueeze(0).repeat(B, 1, 1, 1, 1).contiguous()
+    assert float((m.updateOutput([src, idc]) - src).abs().max()) <= 4e-7 * N
+    # (4) the one-kernel step: forward bits, loss, exact IoU counts, cage gradient against torch's criterion on `ref_out`
+    x = ref_out.clone().requires_grad_(True)
+    ref_loss = torch.nn.functional.smooth_l1_loss(x.double(), tgt.double())
+    ref_loss.backward()
+    _, ref_gc2 = vnn.CageWarpVolumetric(onlyGrid=True).updateGradInput([src, cage], x.grad.float().contiguous())
+    step = vnn.CageWarpSmoothL1Volumetric(keepOutput=True)
+    loss, (_, gc2) = step.forwardBackward([src, cage], tgt)
+    assert torch.equal(step.output, ref_out)
+    assert abs(float(loss) - float(ref_loss.detach())) <= 1e-9 * max(1.0, float(ref_loss.detach()))
+    inter = ((ref_out > 0.5) & (tgt > 0.5)).reshape(B, -1).sum(1)
+    union = ((ref_out > 0.5) | (tgt > 0.5)).reshape(B, -1).sum(1)
+    assert torch.equal(step.iouCounts[:, 0], inter) and torch.equal(step.iouCounts[:, 1], union)
+    assert float((gc2 - ref_gc2).abs().max()) <= 2e-4 * float(ref_gc2.abs().max())
+    # (5) first and last sample against the oracle chain, bit-exact
+    for b in (0, B - 1):
+        assert bits_equal(host(out[b:b + 1]), cage_chain_oracle(src_np[b:b + 1], cage_np[b:b + 1], (N, N, N)))
+    # (6) grid generator folded into the sampler, same size: bits of the two-module chain
+    T = dev(random_affine(B, rng))
+    grid = vnn.VolumetricGridGenerator(N, N, N).updateOutput(T)
+    assert torch.equal(vnn.AffineSamplerVolumetric(N, N, N).updateOutput([src, T]), warp.updateOutput([src, grid]))
