@@ -87,8 +87,22 @@ __global__ void __launch_bounds__(kGGThreads) k_gridgen_fwd(const real *__restri
 }
 
 // stage 1: partial[b][blk][i*4 + j] = sum over this block's rows of gradGrid[b,v,i] * base[v,j]
+// Tunables of the backward, swept on a B200 at 64^3 x 64 (tools/ggbench.py, profiles/r01_gridgen_backward.txt): rows of
+// loads in flight per warp trip, resident CTAs per SM (a 64-register cap) and waves of CTAs over the batch.
+//   4 / none (80 registers, 3 CTAs) / 4 waves : 90 us      4 / 4 / 4 : 74 us      4 / 4 / 2 : 70 us      4 / 4 / 1 : 65.5 us
+//   8 rows in flight: 84-141 us (registers)      caps of 5, 6, 8 CTAs: 92-174 us (spills)
+// One wave of long-lived CTAs also leaves fewer partials for the ordered final stage.
+#ifndef GG_RPT
+#define GG_RPT 4
+#endif
+#ifndef GG_CTAS
+#define GG_CTAS 4
+#endif
+#ifndef GG_WAVES
+#define GG_WAVES 1
+#endif
 template <typename real>
-__global__ void __launch_bounds__(kGGThreads) k_gridgen_bwd_partial(const real *__restrict__ gg,
+__global__ void __launch_bounds__(kGGThreads, GG_CTAS) k_gridgen_bwd_partial(const real *__restrict__ gg,
                                                                     double *__restrict__ partial, int D, int H,
                                                                     int W, int rows_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(kGGThreads) k_gridgen_bwd_partial(const real *
       g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
     }
   };
-  constexpr int kRowsPerTrip = 4;
+  constexpr int kRowsPerTrip = GG_RPT;
   for (; r < r_end; r += kRowsPerTrip) {
     for (int x = lane; x < W; x += 32) {
       real g[kRowsPerTrip][4];
@@ -183,8 +197,8 @@ __global__ void k_gridgen_bwd_final(const double *__restrict__ partial, real *__
 namespace {
 int bwd_blocks_per_sample(int64_t B, int64_t D, int64_t H, int *rows_per_warp) {
   const int64_t rows = D * H;
-  // aim for ~4 waves of 148 SMs x 3 CTAs (80 registers) over the whole batch, at least 4 rows per warp
-  int64_t want_blocks = (int64_t)kSMs * 3 * 4 / (B > 0 ? B : 1);
+  // one wave of 148 SMs x 4 resident CTAs over the whole batch (see the sweep above), at least 4 rows per warp
+  int64_t want_blocks = (int64_t)kSMs * (GG_CTAS > 1 ? GG_CTAS : 3) * GG_WAVES / (B > 0 ? B : 1);
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpw = (rows + want_blocks * kGGWarps - 1) / (want_blocks * kGGWarps);
   if (rpw < 4) rpw = 4;
