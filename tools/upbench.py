@@ -5,7 +5,7 @@ import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from alignet_b200 import _abi, synth, nn as vnn
-N, B = 64, 64
+N, B = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 64)
 rng = np.random.default_rng(7)
 def timed(fn, k=5):
     for _ in range(2): fn()
@@ -17,11 +17,11 @@ def timed(fn, k=5):
     return e0.elapsed_time(e1) / k * 1e3
 field_i = vnn.VolumetricGridGenerator(N, N, N).updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))
 gfield = torch.randn((B, N, N, N, 4), device="cuda"); gfield[..., 3] = 0
-for csz in (4, 8, 12):
+for csz in (4, 8, 12, 16):
     cage = torch.from_numpy(synth.alignet_cage(8, csz, rng).astype(np.float32)).cuda().repeat(B // 8, 1, 1, 1, 1).contiguous()
     cage_vol = torch.ones((B, csz, csz, csz, 4), device="cuda"); cage_vol[..., :3] = cage.permute(0, 2, 3, 4, 1)
     ref = None
-    for algo, nm in ((_abi.ALGO_DIRECT, "direct"), (_abi.ALGO_TILE, "tile")):
+    for algo, nm in ((_abi.ALGO_DIRECT, "direct"), (_abi.ALGO_TILE, "tile"), (_abi.ALGO_AUTO, "auto")):
         for ov in (True, False):
             m = vnn.BilinearSamplerVolumetric(onlyVolume=ov, algo=algo)
             us = timed(lambda: m.updateGradInput([cage_vol, field_i], gfield))
