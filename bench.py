@@ -587,6 +587,21 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         "hbm_not_allocated_mib": 2 * V * 16 / 2 ** 20}
     del field, field_i, gfield, cage_vol
 
+    # ---- the reference's own graph: backward of the cage up-sample (a csz^3 x 4 volume under the full-resolution field) ------
+    res["small_volume_backward"] = {
+        "what": "BilinearSamplerVolumetric updateGradInput (gradInput[1] only) with a csz^3 x 4 cage volume and the identity field: "
+                "direct kernel (VOLSTN_ALGO_DIRECT) vs the automatic choice (privatised, warp-aggregated)"}
+    gf = torch.randn((B, N, N, N, 4), device="cuda")
+    gf[..., 3] = 0
+    fi = vnn.VolumetricGridGenerator(N, N, N).updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))
+    for c in (4, 8):
+        cv = torch.rand((B, c, c, c, 4), device="cuda")
+        md, ma = vnn.BilinearSamplerVolumetric(onlyVolume=True, algo=_abi.ALGO_DIRECT), vnn.BilinearSamplerVolumetric(onlyVolume=True)
+        d_ms = timed(lambda: md.updateGradInput([cv, fi], gf), k=2)
+        a_ms = timed(lambda: ma.updateGradInput([cv, fi], gf), k=5)
+        res["small_volume_backward"][f"cage_{c}"] = {"direct_ms": d_ms, "auto_ms": a_ms, "speedup": d_ms / a_ms}
+    del gf, fi
+
     # ---- f4: the whole training step of the warp head (forward + SmoothL1 + IoU + backward) in one kernel ----------
     target = rep(synth.volume("v2", nb, N, N, N, 1, rng))
     step = vnn.CageWarpSmoothL1Volumetric()
