@@ -472,6 +472,26 @@ unsigned ctas_per_sample(long long n, int vpt) {
   return (unsigned)((n + (long long)kThreads * vpt - 1) / ((long long)kThreads * vpt));
 }
 
+// gridDim.y: how many samples are walked side by side; a CTA then loops over the samples b, b + gridDim.y, ...  About
+// 16 K CTAs per launch instead of one CTA per 512 voxels of the whole batch (32 K at 64^3 x 64) is 2-10 % faster on a
+// B200 -- forward 83.4 -> 78.7 us, backward 190.3 -> 186.4 us at 64^3 x 64, C = 1; 181 -> 163 us and 558 -> 516 us at C = 4;
+// 184 -> 164 us and 596 -> 544 us at 128^3 x 8, C = 4; fewer than 8 K CTAs loses again (profiles/r01_kbench_history.txt,
+// section batch_rows).  The number of rounds is an integer so that every CTA walks the same number of samples (+-1).
+unsigned batch_rows(int B, unsigned blocks_x) {
+  const long long kTargetCtas = 16384;
+  long long rounds = ((long long)B * blocks_x + kTargetCtas - 1) / kTargetCtas;
+  if (rounds < 1) rounds = 1;
+  long long by = (B + rounds - 1) / rounds;
+  if (const char *e = getenv("VOLSTN_BY")) {  // tuning only
+    const long long v = atoll(e);
+    if (v >= 1) by = v;
+  }
+  if (by > B) by = B;
+  if (by > 65535) by = 65535;
+  if (by < 1) by = 1;
+  return (unsigned)by;
+}
+
 int pick_vpt(unsigned flags, int C, long long n) {
   int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);
   if (vpt == 1 || vpt == 2 || vpt == 4) return vpt;
@@ -483,7 +503,7 @@ int pick_vpt(unsigned flags, int C, long long n) {
 template <int CT, int G>
 int launch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   dim3 block(kThreads);
-  const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  const unsigned by = batch_rows(a.B, ctas_per_sample(a.n, vpt));
   auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 4: k_sampler_fwd_packed<float, CT, G, 4><<<dim3(blocks_x(4), by), block, 0, st>>>(a); break;
@@ -526,7 +546,7 @@ int launch_fwd_generic(const SamplerArgs<real> &a, int G, cudaStream_t st) {
 template <int CT, int G, bool OG, bool OV>
 int launch_bwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   dim3 block(kThreads);
-  const unsigned by = (unsigned)(a.B < 65535 ? a.B : 65535);
+  const unsigned by = batch_rows(a.B, ctas_per_sample(a.n, vpt));
   auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 2:
