@@ -53,6 +53,7 @@ SIGNATURES = {
     "volstn_b200_cage_warp_forward": (_i, [_i, _vp, _pi64, _P5, _P5, _u, _vp]),
     "volstn_b200_cage_warp_backward": (_i, [_i, _vp, _pi64, _P5, _P5, _vp, _P5, _u, _vp]),
     "volstn_b200_cage_warp_step": (_i, [_i, _vp, _pi64, _P5, _P5, _P5, _P5, _vp, _vp, _vp, ctypes.c_float, _u, _vp]),
+    "volstn_b200_sampler_step": (_i, [_i, _i, _P5, _P5, _P5, _P5, _P5, _P5, _vp, _vp, ctypes.c_float, _u, _vp]),
     "volstn_b200_gridgen_forward": (_i, [_i, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "volstn_b200_gridgen_backward": (_i, [_i, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "volstn_b200_gridgen_backward_workspace": (_sz, [_i64, _i64, _i64, _i64]),

@@ -368,4 +368,66 @@ int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_d
   return row_cage_step(a, p, a.s.B, og, st);
 }
 
+// the same step for the plain sampler: the sampling grid is a tensor (any strides; G = 4 or 3) and its gradient is stored
+int volstn_b200_sampler_step(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                             const volstn_tensor5 *target, const volstn_tensor5 *out, const volstn_tensor5 *gradVol,
+                             const volstn_tensor5 *gradGrid, double *loss_sum, uint64_t *iou_counts, float grad_scale,
+                             unsigned flags, void *cuda_stream) {
+  int rc = check_fused(dtype, vol, target);
+  if (rc) return rc;
+  if (G != 3 && G != 4) return VOLSTN_ERR_ARG;
+  if (!grid || !gradGrid) return VOLSTN_ERR_ARG;
+  if (flags & VOLSTN_BWD_ONLY_VOLUME) return VOLSTN_ERR_ARG;
+  const bool og = flags & VOLSTN_BWD_ONLY_GRID;
+  if (vol->size[4] != 1) return VOLSTN_ERR_UNSUPPORTED;
+  if (grid->size[0] != vol->size[0] || grid->size[4] != G) return VOLSTN_ERR_SHAPE;  // lua:33-34
+  for (int i = 0; i < 5; i++)
+    if (gradGrid->size[i] != grid->size[i]) return VOLSTN_ERR_SHAPE;
+  for (int i = 0; i < 4; i++)
+    if (target->size[i] != grid->size[i]) return VOLSTN_ERR_SHAPE;  // lua:36-41
+  if (out)
+    for (int i = 0; i < 5; i++)
+      if (out->size[i] != target->size[i] || (target->size[i] > 1 && out->stride[i] != target->stride[i]))
+        return VOLSTN_ERR_LAYOUT;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int64_t B = vol->size[0];
+  if (!og) {
+    if (!gradVol) return VOLSTN_ERR_ARG;
+    for (int i = 0; i < 5; i++)
+      if (gradVol->size[i] != vol->size[i]) return VOLSTN_ERR_SHAPE;
+    if ((flags & VOLSTN_BWD_ZERO_GRADVOL) && desc_numel(gradVol) && (rc = zero_grad_vol(gradVol, st))) return rc;
+  }
+  if (B == 0) return VOLSTN_OK;
+  if (!loss_sum) return VOLSTN_ERR_ARG;
+  VOLSTN_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, (size_t)B * sizeof(double), st));
+  if (iou_counts) VOLSTN_CUDA_TRY(cudaMemsetAsync(iou_counts, 0, (size_t)B * 2 * sizeof(uint64_t), st));
+  if (desc_numel(target) == 0) return VOLSTN_OK;
+  if (out && !out->data) return VOLSTN_ERR_ARG;
+  RowArgs a;
+  RowPlan p;
+  zero_args(a);
+  memset(&p, 0, sizeof(p));
+  p.src = ROW_SRC_GRID;
+  if (!plan_volume(a, p, vol, target, og ? nullptr : gradVol) || !row_tensor_ok(grid) || !row_tensor_ok(gradGrid))
+    return VOLSTN_ERR_LAYOUT;
+  if (!p.c1) return VOLSTN_ERR_LAYOUT;
+  a.s.grid = static_cast<const float *>(grid->data);
+  a.s.gout = static_cast<const float *>(target->data);
+  a.s.out = out ? static_cast<float *>(out->data) : nullptr;
+  a.s.ggrid = static_cast<float *>(gradGrid->data);
+  a.gB = grid->stride[0];
+  a.gD = (int)grid->stride[1], a.gH = (int)grid->stride[2], a.gW = (int)grid->stride[3], a.gC = (int)grid->stride[4];
+  a.ggB = gradGrid->stride[0];
+  a.ggD = (int)gradGrid->stride[1], a.ggH = (int)gradGrid->stride[2], a.ggW = (int)gradGrid->stride[3];
+  a.ggC = (int)gradGrid->stride[4];
+  a.g3 = G == 3;
+  p.grid_aos4 = G == 4 && aos4(grid) && aos4(gradGrid);
+  a.loss_norm = grad_scale;
+  a.loss = loss_sum;
+  a.iou = reinterpret_cast<unsigned long long *>(iou_counts);
+  plan_debug_flags(a, flags);
+  plan_geometry(a, p);
+  return row_cage_step(a, p, a.s.B, og, st);
+}
+
 }  // extern "C"

@@ -311,7 +311,7 @@ __device__ __forceinline__ void row_voxel_backward(const RowArgs &a, const Voxel
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = (FAST || s.in(k)) ? __ldg(rows.p[k >> 1] + ((k & 1) ? sW : 0) + co) : 0.f;
       if constexpr (LOSS) {
-        const float o = sum8<0>(cw, v);  // the forward value, bit for bit (...c:566-573)
+        const float o = a.g3 ? sum8<1>(cw, v) : sum8<0>(cw, v);  // the forward value, bit for bit (...c:566-573 / 149-156)
         const float x = __fsub_rn(o, go);
         *fwd = o, *tgt = go;
         go = x < -1.0f ? -a.loss_norm : (x > 1.0f ? a.loss_norm : __fmul_rn(a.loss_norm, x));
@@ -815,9 +815,24 @@ int row_backward(const RowArgs &a, const RowPlan &p, int B, bool og, bool ov, cu
   }
 }
 
-// fused training step of the cage warp: forward + SmoothL1 + backward in one pass (single channel)
+// fused training step: forward + SmoothL1 + backward in one pass (single channel); cage source or grid tensor
 int row_cage_step(const RowArgs &a, const RowPlan &p, int B, bool og, cudaStream_t st) {
-  if (!p.c1 || p.src != ROW_SRC_CAGE) return VOLSTN_ERR_UNSUPPORTED;
+  if (!p.c1) return VOLSTN_ERR_UNSUPPORTED;
+  if (p.src == ROW_SRC_GRID) {
+    if (p.grid_aos4) {
+      if (og)
+        return p.two_rows ? launch_bwd<ROW_SRC_GRID, true, true, true, true, false, true>(a, B, st)
+                          : launch_bwd<ROW_SRC_GRID, true, true, false, true, false, true>(a, B, st);
+      return p.two_rows ? launch_bwd<ROW_SRC_GRID, true, true, true, false, false, true>(a, B, st)
+                        : launch_bwd<ROW_SRC_GRID, true, true, false, false, false, true>(a, B, st);
+    }
+    if (og)
+      return p.two_rows ? launch_bwd<ROW_SRC_GRID, false, true, true, true, false, true>(a, B, st)
+                        : launch_bwd<ROW_SRC_GRID, false, true, false, true, false, true>(a, B, st);
+    return p.two_rows ? launch_bwd<ROW_SRC_GRID, false, true, true, false, false, true>(a, B, st)
+                      : launch_bwd<ROW_SRC_GRID, false, true, false, false, false, true>(a, B, st);
+  }
+  if (p.src != ROW_SRC_CAGE) return VOLSTN_ERR_UNSUPPORTED;
   if (og)
     return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, true, false, true>(a, B, st)
                       : launch_bwd<ROW_SRC_CAGE, false, true, false, true, false, true>(a, B, st);

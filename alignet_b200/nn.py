@@ -30,7 +30,8 @@ from . import _abi
 from ._abi import Tensor5
 
 __all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
-           "AffineSamplerVolumetric", "CageWarpVolumetric", "CageWarpSmoothL1Volumetric"]
+           "AffineSamplerVolumetric", "CageWarpVolumetric", "CageWarpSmoothL1Volumetric",
+           "BilinearSamplerSmoothL1Volumetric"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -688,3 +689,49 @@ class CageWarpSmoothL1Volumetric(Module):
         """computeIOU (util.lua:118-119): mean over the batch of intersection / union"""
         c = self.iouCounts.to(torch.float64)
         return (c[:, 0] / c[:, 1]).sum() / c.size(0)
+
+
+class BilinearSamplerSmoothL1Volumetric(Module):
+    """``nn.BilinearSamplerVolumetric`` + ``nn.SmoothL1Criterion`` + ``computeIOU`` as one training-step kernel, for
+    models that emit a dense sampling field: ``forwardBackward({volume, grids}, target) -> (loss, {gradVolume, gradGrids})``.
+    Same conventions as :class:`CageWarpSmoothL1Volumetric`; single-channel CUDA float volumes, ``B x D x H x W x G`` grids."""
+
+    def __init__(self, gridWidth: int = 4, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False):
+        super().__init__()
+        assert gridWidth in (3, 4)
+        self.gridWidth, self.sizeAverage, self.onlyGrid, self.keepOutput = gridWidth, sizeAverage, onlyGrid, keepOutput
+        self.gradInput = []
+        self.loss = self.lossPerSample = self.iouCounts = None
+
+    def forwardBackward(self, input, target):
+        vol, grid = input[0], input[1]
+        assert vol.is_cuda and vol.dim() == 5 and vol.is_contiguous() and vol.size(4) == 1
+        assert grid.dim() == 5 and grid.size(0) == vol.size(0) and grid.size(4) == self.gridWidth
+        assert target.dim() == 5 and tuple(target.shape[:4]) == tuple(grid.shape[:4]) and target.size(4) == 1
+        _same_place(vol, grid, target)
+        B, n = vol.size(0), target.numel()
+        target = target if target.is_contiguous() else target.contiguous()
+        out = torch.empty_like(target) if self.keepOutput else None
+        gv = torch.empty_like(vol)
+        gg = torch.empty(tuple(grid.shape), dtype=grid.dtype, device=grid.device)
+        loss_sum = torch.empty((B,), dtype=torch.float64, device=vol.device)
+        iou = torch.empty((B, 2), dtype=torch.int64, device=vol.device)
+        norm = float(torch.tensor(1.0 / float(torch.tensor(float(n), dtype=torch.float32)), dtype=torch.float32)) if self.sizeAverage else 1.0
+        flags = _abi.BWD_ZERO_GRADVOL
+        if self.onlyGrid:
+            flags |= _abi.BWD_ONLY_GRID
+            gv.zero_()
+        _require_device(vol.device.index)
+        with torch.cuda.device(vol.device):
+            rc = _abi.lib().volstn_b200_sampler_step(_dtype_code(vol), self.gridWidth, _desc(vol), _desc(grid), _desc(target),
+                                                     _desc(out) if out is not None else None, _desc(gv), _desc(gg),
+                                                     loss_sum.data_ptr(), iou.data_ptr(), ctypes.c_float(norm), flags,
+                                                     _stream(vol))
+        _abi.check(rc, "BilinearSamplerSmoothL1Volumetric_forwardBackward")
+        self.lossPerSample, self.iouCounts = loss_sum, iou
+        self.loss = loss_sum.sum() / n if self.sizeAverage else loss_sum.sum()
+        self.output = out if out is not None else torch.empty(0)
+        self.gradInput = [gv, gg]
+        return self.loss, self.gradInput
+
+    iou = CageWarpSmoothL1Volumetric.iou

@@ -629,7 +629,25 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         "fused_modules_plus_elementwise_criterion_ms": c_s, "one_kernel_ms": f_s, "speedup": c_s / f_s,
         "voxels_per_s": V / (f_s * 1e-3), "bytes_per_voxel": 8,
         "vs_unfused_module_chain": (res["cage_warp"]["chain"]["fwd_ms"] + res["cage_warp"]["chain"]["bwd_ms"] + (c_s - f_f - f_b)) / f_s}
-    del target
+    # the same one-kernel step for the plain sampler (a dense field tensor), identity field
+    gridn0 = rep(synth.grid("g1", nb, N, N, N, rng))
+    smp_og, sstep = vnn.BilinearSamplerVolumetric(onlyGrid=True), vnn.BilinearSamplerSmoothL1Volumetric()
+
+    def chain_sampler_step():
+        o = smp_og.updateOutput([vol, gridn0])
+        x = o - target
+        loss = torch.where(x.abs() < 1, 0.5 * x * x, x.abs() - 0.5).sum()
+        smp_og.updateGradInput([vol, gridn0], x.clamp(-1, 1) / o.numel())
+        return loss
+
+    c_s = timed(chain_sampler_step)
+    f_s = timed(lambda: sstep.forwardBackward([vol, gridn0], target))
+    res["sampler_step"] = {
+        "what": "BilinearSamplerVolumetric forward + SmoothL1Criterion forward/backward + computeIOU + backward (gradGrid only), grid tensor given",
+        "modules_plus_elementwise_criterion_ms": c_s, "one_kernel_ms": f_s, "speedup": c_s / f_s,
+        "voxels_per_s": V / (f_s * 1e-3), "bytes_per_voxel": 16 + 4 + 4 + 16,
+        "frac_of_hbm_peak": 40 * V / (f_s * 1e-3) / 1e9 / peak}
+    del target, gridn0
 
     # ---- f3: grid generator folded into the sampler ----------------------------------------------------------
     T = torch.eye(4, device="cuda").repeat(B, 1, 1) + 0.02 * torch.randn(B, 4, 4, device="cuda")

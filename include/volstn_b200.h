@@ -175,6 +175,14 @@ int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_d
                                void *gradCage, double *loss_sum, uint64_t *iou_counts, float grad_scale, unsigned flags,
                                void *cuda_stream);
 
+/* The same step for the plain sampler (a network that emits a dense field): out = sampler_forward(vol, grid), loss,
+ * gradOut, gradVol / gradGrid = sampler_backward -- one pass, single-channel volumes, any strides, G = 4 or 3.
+ * gradGrid is assigned; flags, loss_sum, iou_counts, grad_scale and `out` as for volstn_b200_cage_warp_step. */
+int volstn_b200_sampler_step(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
+                             const volstn_tensor5 *target, const volstn_tensor5 *out, const volstn_tensor5 *gradVol,
+                             const volstn_tensor5 *gradGrid, double *loss_sum, uint64_t *iou_counts, float grad_scale,
+                             unsigned flags, void *cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Grid generator (nn.VolumetricGridGenerator), DEVICE pointers, contiguous tensors
  * ------------------------------------------------------------------------------------------- */

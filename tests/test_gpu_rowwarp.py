@@ -462,3 +462,31 @@ def test_fused_modules_at_full_size(N, B, csz):
     T = dev(random_affine(B, rng))
     grid = vnn.VolumetricGridGenerator(N, N, N).updateOutput(T)
     assert torch.equal(vnn.AffineSamplerVolumetric(N, N, N).updateOutput([src, T]), warp.updateOutput([src, grid]))
+
+
+@pytest.mark.parametrize("G", [4, 3])
+@pytest.mark.parametrize("oshape", [(7, 10, 37), (6, 9, 20)])
+def test_sampler_smooth_l1_step(G, oshape):
+    """the one-kernel step with a grid tensor: forward bits, loss, exact IoU counts, gradGrid bit-exact against the
+    oracle fed with the criterion's gradient, gradVol within 1e-4"""
+    rng = np.random.default_rng(97 + G + oshape[2])
+    B, ishape = 3, (8, 9, 11)
+    vol = synth.volume("v2", B, *ishape, 1, rng)
+    vol[1] *= 3.0
+    target = synth.volume("v2", B, *oshape, 1, rng)
+    for gk in ("g1", "g2", "g4"):
+        grid = synth.grid(gk, B, *oshape, rng, G=G, csz=4)
+        ref_out = oracle.sampler_forward(vol, grid, G)
+        go = oracle.smooth_l1_backward(ref_out, target)
+        ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go, G)
+        for only_grid in (True, False):
+            m = vnn.BilinearSamplerSmoothL1Volumetric(gridWidth=G, onlyGrid=only_grid, keepOutput=True)
+            loss, (gv, gg) = m.forwardBackward([dev(vol), dev(grid)], dev(target))
+            assert bits_equal(host(m.output), ref_out), gk
+            assert abs(float(loss) - oracle.smooth_l1_forward(ref_out, target)) <= 1e-9
+            assert np.array_equal(m.iouCounts.cpu().numpy().astype(np.uint64), oracle.iou_counts(ref_out, target))
+            assert bits_equal(host(gg), ref_gg), (gk, describe_mismatch(host(gg), ref_gg))
+            if only_grid:
+                assert float(gv.abs().max()) == 0.0
+            else:
+                assert max_rel(host(gv), ref_gv) <= 1e-4
