@@ -490,3 +490,24 @@ def test_sampler_smooth_l1_step(G, oshape):
                 assert float(gv.abs().max()) == 0.0
             else:
                 assert max_rel(host(gv), ref_gv) <= 1e-4
+
+
+def test_fused_modules_match_the_reference_chain_golden():
+    """tests/golden/cage_warp_golden.npz: chains of the reference's own compiled C code (make_cage_golden.py)"""
+    from tests.test_oracle_golden import load_cage_golden
+    for name, c in load_cage_golden().items():
+        src, cage, go = c["source"], c["cage"], c["gradOut"]
+        oshape = c["out"].shape[1:4]
+        m = vnn.CageWarpVolumetric(*oshape)
+        out = host(m.updateOutput([dev(src), dev(cage)]))
+        assert bits_equal(out, c["out"]), (name, describe_mismatch(out, c["out"]))
+        gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+        assert max_rel(host(gsrc), c["gradSource"]) <= 1e-4, name
+        assert max_rel(host(gcage), c["gradCage"]) <= 1e-4, name
+        if "step_loss" in c:
+            step = vnn.CageWarpSmoothL1Volumetric(onlyGrid=False, keepOutput=True)  # output resolution = the target's
+            loss, (gs, gc) = step.forwardBackward([dev(src), dev(cage)], dev(c["target"]))
+            assert bits_equal(host(step.output), c["out"]), name
+            assert abs(float(loss) - float(c["step_loss"])) <= 1e-9 * max(1.0, float(c["step_loss"]))
+            assert np.array_equal(step.iouCounts.cpu().numpy().astype(np.uint64), c["step_iou"]), name
+            assert max_rel(host(gc), c["step_gradCage"]) <= 1e-4 and max_rel(host(gs), c["step_gradSource"]) <= 1e-4, name
