@@ -160,3 +160,21 @@ def test_alignet_initial_cage_warps_to_identity():
     rng = np.random.default_rng(4)
     src = synth.volume("v1", 1, N, N, N, 1, rng)
     assert np.max(np.abs(oracle.sampler_forward(src, field) - src)) < 2e-5
+
+
+def test_cumsum_restatement_agrees_with_aten_cpu():
+    """Torch7's TH cumsum is not vendored (parity unpinned).  ATen's CPU cumsum is its direct descendant and keeps the
+    semantics the restatement assumes (float accumulated in double, each prefix rounded to float): bit-for-bit equal."""
+    import torch
+    rng = np.random.default_rng(31)
+    x = (10 * rng.standard_normal((3, 3, 7, 8, 9))).astype(np.float32)
+    ref = oracle.cumsum_forward(x)
+    for i in range(3):
+        got = torch.cumsum(torch.from_numpy(x[:, i]), dim=1 + i).numpy()
+        assert np.array_equal(got.view(np.uint32), ref[:, i].view(np.uint32)), i
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    refb = oracle.cumsum_backward(g)
+    for i in range(3):
+        t = torch.from_numpy(g[:, i])
+        got = torch.flip(torch.cumsum(torch.flip(t, [1 + i]), dim=1 + i), [1 + i]).numpy()   # Cumsum.lua:44-47
+        assert np.array_equal(got.view(np.uint32), refb[:, i].view(np.uint32)), i
