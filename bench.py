@@ -355,8 +355,32 @@ def run_ours(a):
             # follows forward on the same input, VOLSTN_HOST_REUSE_INPUTS) and uploads only gradOut
             h2d = (vol_h.numel() + grid_h.numel()) * esz + go_h.numel() * esz
             d2h = (go_h.numel() + vol_h.numel() + grid_h.numel()) * esz
+            # the host link itself (pinned 256 MiB copies, one direction at a time): the two calls of a step are
+            # synchronous, so the step cannot beat  upload(volume + grid) + download(gradVolume + gradGrid)
+            link = None
+            try:
+                nlk = 256 << 20
+                hb = torch.empty(nlk, dtype=torch.uint8).pin_memory()
+                db = torch.empty(nlk, dtype=torch.uint8, device="cuda")
+
+                def one_way(up):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(4):
+                        (db.copy_(hb, non_blocking=True) if up else hb.copy_(db, non_blocking=True))
+                    torch.cuda.synchronize()
+                    return nlk * 4 / (time.perf_counter() - t0) / 1e9
+
+                one_way(True), one_way(False)
+                up_gbs, down_gbs = one_way(True), one_way(False)
+                lb_ms = ((vol_h.numel() + grid_h.numel()) * esz / up_gbs + (vol_h.numel() + grid_h.numel()) * esz / down_gbs) / 1e6
+                link = {"h2d_gbs": up_gbs, "d2h_gbs": down_gbs, "lower_bound_ms_per_step": lb_ms, "frac_of_link_bound": lb_ms / (e2e_s * 1e3),
+                        "note": "forward is bound by uploading volume + grid, backward by downloading gradVolume + gradGrid; the smaller transfers overlap"}
+                del hb, db
+            except Exception as e:  # noqa: BLE001
+                link = {"error": repr(e)[:200]}
             e2e = {"value": V * n_gpus / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "link": link,
                    "path": "volstn_b200_host_sampler_forward/backward: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors; backward re-uses the forward call's device copies of volume and grid"}
     clocks = sampler.summary()
 
