@@ -91,3 +91,58 @@ def test_host_backward_reuses_forward_inputs():
     grid[..., :3] *= 0.5                                       # in-place edit after forward
     gv4, gg4 = m2.updateGradInput([vol, grid], go)
     assert bits_equal(gg4.numpy(), rgg2)
+
+
+def test_host_calls_from_concurrent_threads():
+    """The reference's loader threads call the sampler concurrently on CPU tensors (data.lua:11-24,
+    dataset_2d.lua:293-306).  The library is re-entrant with one staging context per thread (nn.py keeps them in
+    thread-local storage); device-pointer calls on separate streams are independent as well."""
+    import threading
+    rng = np.random.default_rng(9)
+    jobs = []
+    for i in range(6):
+        B, N = 3 + i, 12 + i
+        vol = synth.volume("v1", B, N, N, N, 1, rng)
+        grid = synth.grid("g4", B, N, N, N, rng)
+        go = synth.grad_output(B, N, N, N, 1, rng)
+        T = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+        T[:, :3, 3] = 0.1 * rng.standard_normal((B, 3)).astype(np.float32)
+        jobs.append((vol, grid, go, T))
+    results, errors = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            vol, grid, go, T = jobs[i]
+            for _ in range(3):  # repeated calls reuse the thread's context
+                if i % 2 == 0:  # host tensors
+                    m = vnn.BilinearSamplerVolumetric()
+                    out = m.updateOutput([torch.from_numpy(vol), torch.from_numpy(grid)]).clone()
+                    gv, gg = m.updateGradInput([torch.from_numpy(vol), torch.from_numpy(grid)], torch.from_numpy(go))
+                    aff = vnn.AffineSamplerVolumetric(*vol.shape[1:4]).updateOutput([torch.from_numpy(vol), torch.from_numpy(T)])
+                else:           # device tensors on this thread's own stream
+                    st = torch.cuda.Stream()
+                    with torch.cuda.stream(st):
+                        m = vnn.BilinearSamplerVolumetric()
+                        tv, tg, tgo = torch.from_numpy(vol).cuda(), torch.from_numpy(grid).cuda(), torch.from_numpy(go).cuda()
+                        out = m.updateOutput([tv, tg]).clone()
+                        gv, gg = m.updateGradInput([tv, tg], tgo)
+                        aff = vnn.AffineSamplerVolumetric(*vol.shape[1:4]).updateOutput([tv, torch.from_numpy(T).cuda()])
+                    st.synchronize()
+                results[i] = (out.cpu().numpy(), gv.cpu().numpy(), gg.cpu().numpy(), aff.cpu().numpy())
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, (vol, grid, go, T) in enumerate(jobs):
+        out, gv, gg, aff = results[i]
+        assert bits_equal(out, oracle.sampler_forward(vol, grid)), i
+        rgv, rgg = oracle.sampler_backward(vol, grid, go)
+        assert bits_equal(gg, rgg), i
+        assert max_rel(gv, rgv) <= 1e-4, i
+        agrid = vnn.VolumetricGridGenerator(*vol.shape[1:4]).updateOutput(torch.from_numpy(T).cuda()).cpu().numpy()
+        assert bits_equal(aff, oracle.sampler_forward(vol, agrid)), i
