@@ -36,6 +36,8 @@ struct RowSmem {
   float *tz, *ty, *tx;
   int *iz, *iy, *ix;
   float4 *cg;    // CAGE: (cD+1) x (cH+1) x (cW+1) cells (z, y, x, 1), one layer of zeros on every high face
+  float2 *cgzy;  // ROW_CAGE_SPLIT: the same cells as (z, y) pairs ...
+  float *cgx;    // ... and x values (8 + 4 byte loads: 3 shared-memory wavefronts per corner instead of 4)
   float *gc;     // CAGE backward: gradient of the cage, same cells x 3
   int *xs;       // CAGE backward: xs[t] = first x whose low cage cell is >= t  (t = 0 .. cW)
   float *stage;  // CAGE backward: per warp, per slot: 6 x oWp products (wx * gg[c], (1 - wx) * gg[c])
@@ -67,6 +69,8 @@ __device__ __forceinline__ void row_carve(RowSmem &m, unsigned char *raw, const 
     m.tx = m.ty + oH;
   } else if constexpr (SRC == ROW_SRC_CAGE) {
     m.cg = reinterpret_cast<float4 *>(raw);
+    m.cgzy = reinterpret_cast<float2 *>(raw);
+    m.cgx = reinterpret_cast<float *>(m.cgzy + row_cells(a));
     m.tz = reinterpret_cast<float *>(m.cg + row_cells(a));
     m.ty = m.tz + oD;
     m.tx = m.ty + oH;
@@ -105,7 +109,12 @@ __device__ __forceinline__ void row_fill(const RowSmem &m, const RowArgs &a, int
         const long long o = ((long long)z * a.cH + y) * a.cW + x;
         v = make_float4(__ldg(cb + o), __ldg(cb + plane + o), __ldg(cb + 2 * plane + o), 1.0f);
       }
+#if ROW_CAGE_SPLIT
+      m.cgzy[i] = make_float2(v.x, v.y);
+      m.cgx[i] = v.z;
+#else
       m.cg[i] = v;
+#endif
       if constexpr (BWD) m.gc[3 * i] = m.gc[3 * i + 1] = m.gc[3 * i + 2] = 0.f;
     }
     // the sampler's own set-up (...c:507-517) of the identity coordinate of every axis position: with the identity
@@ -155,13 +164,20 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
   const float wxs[2] = {wx, __fsub_rn(1.0f, wx)};
   const float wys[2] = {wy, __fsub_rn(1.0f, wy)};
   const float wzs[2] = {wz, __fsub_rn(1.0f, wz)};
-  const float4 *c0 = m.cg + (m.iz[z] * (a.cH + 1) + m.iy[y]) * cWp + m.ix[x];
+  const int cbase = (m.iz[z] * (a.cH + 1) + m.iy[y]) * cWp + m.ix[x];
   float az = 0.f, ay = 0.f, ax = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const float w = __fmul_rn(__fmul_rn(wxs[k & 1], wys[(k >> 1) & 1]), wzs[k >> 2]);
-    const float4 v = c0[(k & 1) + ((k >> 1) & 1) * cWp + (k >> 2) * cHWp];
+    const int ci = cbase + (k & 1) + ((k >> 1) & 1) * cWp + (k >> 2) * cHWp;
+#if ROW_CAGE_SPLIT
+    const float2 vzy = m.cgzy[ci];
+    const float vx = m.cgx[ci];
+    const float pz = __fmul_rn(w, vzy.x), py = __fmul_rn(w, vzy.y), px = __fmul_rn(w, vx);
+#else
+    const float4 v = m.cg[ci];
     const float pz = __fmul_rn(w, v.x), py = __fmul_rn(w, v.y), px = __fmul_rn(w, v.z);
+#endif
     az = k ? __fadd_rn(az, pz) : pz;
     ay = k ? __fadd_rn(ay, py) : py;
     ax = k ? __fadd_rn(ax, px) : px;
@@ -175,6 +191,9 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
 // cage kernels, 87 % busy in profiles/r01_row_kernels.md) are needed for about one row in nine.  Measured on a B200
 // and REJECTED (profiles/r01_fbench_history.txt): the 48 extra registers either spill (caps of 64 / 80 registers:
 // forward 270 / 247 us against 199 us) or halve the occupancy (cap 128: forward 192 us, backward 455 us against 366 us).
+#ifndef ROW_CAGE_SPLIT
+#define ROW_CAGE_SPLIT 0
+#endif
 #ifndef ROW_CAGE_CACHE
 #define ROW_CAGE_CACHE 0
 #endif
