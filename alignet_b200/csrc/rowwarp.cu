@@ -31,6 +31,14 @@ __device__ __forceinline__ float row_base_coord(int k, int n) {
 // ---------------------------------------------------------------------------------------------
 // shared memory
 // ---------------------------------------------------------------------------------------------
+// Cage cells in shared memory as (z, y) pairs plus x values instead of 16-byte (z, y, x, 1) cells: a 16-byte shared load of a
+// warp is four wavefronts whatever the lanes' addresses, an 8-byte one two, a 4-byte one one -- three per corner instead
+// of four.  The L1/LSU pipe is what bounds the cage kernels (87 % busy): forward 198 -> 186 us, full backward 556 -> 537 us
+// at 64^3 x 64 (profiles/r01_fbench_history.txt).
+#ifndef ROW_CAGE_SPLIT
+#define ROW_CAGE_SPLIT 1
+#endif
+
 struct RowSmem {
   // AFFINE: normalised coordinates of the three axes.  CAGE: low-corner index and weight per axis position.
   float *tz, *ty, *tx;
@@ -191,13 +199,6 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
 // cage kernels, 87 % busy in profiles/r01_row_kernels.md) are needed for about one row in nine.  Measured on a B200
 // and REJECTED (profiles/r01_fbench_history.txt): the 48 extra registers either spill (caps of 64 / 80 registers:
 // forward 270 / 247 us against 199 us) or halve the occupancy (cap 128: forward 192 us, backward 455 us against 366 us).
-// Cage cells in shared memory as (z, y) pairs plus x values instead of 16-byte (z, y, x, 1) cells: a 16-byte shared load of a
-// warp is four wavefronts whatever the lanes' addresses, an 8-byte one two, a 4-byte one one -- three per corner instead
-// of four.  The L1/LSU pipe is what bounds the cage kernels (87 % busy): forward 198 -> 186 us, full backward 556 -> 537 us
-// at 64^3 x 64 (profiles/r01_fbench_history.txt).
-#ifndef ROW_CAGE_SPLIT
-#define ROW_CAGE_SPLIT 1
-#endif
 #ifndef ROW_CAGE_CACHE
 #define ROW_CAGE_CACHE 0
 #endif
