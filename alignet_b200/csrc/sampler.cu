@@ -728,7 +728,7 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
       // into 4^3 .. 12^3 cells per sample, models/alignet_2d.lua:136-147) serialises the direct kernel's global
       // reductions on a handful of addresses -- 22.5 ms at 4^3, 3.0 ms at 8^3, 1.15 ms at 12^3 for 64^3 x 64 -- while the
       // privatised kernel folds a brick's 2048 contributions into a few cells first (and warp-aggregates its shared
-      // atomics, sampler_tile.cu): 0.65 / 0.70 / 0.75 ms (tools/upbench.py, profiles/r01_upsample_backward.txt).
+      // atomics, sampler_tile.cu): 0.47 / 0.55 / 0.67 ms (tools/upbench.py, profiles/r01_upsample_backward.txt).
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_AUTO && !og && tile_supported(a) && a.tile_agg)
         return launch_bwd_tile(a, G, ov, st);
       int vpt = (int)((flags & VOLSTN_VPT_MASK) >> VOLSTN_VPT_SHIFT);

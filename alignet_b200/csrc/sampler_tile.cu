@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kTileThreads, 5)
     // (profiles/r01_upsample_backward.txt).  Lanes with the same corner-0 cell are therefore summed with REDUX
     // (the contributions are integers) and one lane per cell issues the atomic.  The groups of a warp execute their
     // REDUX one after the other (different member masks), so this pays only for very few, large groups: taken when
-    // the launch is in the small-volume regime (a.tile_agg, set by the host) AND the warp holds at most three
+    // the launch is in the small-volume regime (a.tile_agg, set by the host) AND the warp holds at most four
     // distinct cells (warp-uniform).  With a threshold of eight cells the 12^3 cage lost 20 %; sheared fields on
     // large volumes never enter (no MATCH).
     // (REDUX with a partial member mask is emulated by a loop -- 940 instructions per voxel-warp -- so each of the
@@ -175,28 +175,69 @@ __global__ void __launch_bounds__(kTileThreads, 5)
       lead = (int)(threadIdx.x & 31) == leader;
       const unsigned leaders = __ballot_sync(0xffffffffu, lead);
       gid = __popc(leaders & ((1u << leader) - 1u));
-      ngroups = __popc(leaders) <= 3 ? __popc(leaders) : 0;
+      ngroups = __popc(leaders) <= 4 ? __popc(leaders) : 0;
     }
+    // one straight-line body per group count (warp-uniform switch): a loop over the groups with its tests inside cost
+    // 1 000 instructions per voxel-warp (profiles/r01_upsample_backward.txt)
+    auto contribution = [&](int k, int t) {
+      const float c = E::mul(cw[k], go[t]);  // ...c:737, the reference's product (0 for tail threads)
+      // round(c * scale) without a conversion instruction: |c * scale| < 2^21, so adding 1.5 * 2^23
+      // leaves the integer in the mantissa
+      return __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000;
+    };
+    auto cell_of = [&](int k) { return s_gv + t0 + ((k & 1) ? CT : 0) + ((k & 2) ? ty : 0) + ((k & 4) ? tz : 0); };
+    if (ngroups == 1) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      int *cell = s_gv + t0 + ((k & 1) ? CT : 0) + ((k & 2) ? ty : 0) + ((k & 4) ? tz : 0);
+      for (int k = 0; k < 8; k++) {
+        int *cell = cell_of(k);
 #pragma unroll
-      for (int t = 0; t < CT; t++) {
-        const float c = E::mul(cw[k], go[t]);  // ...c:737, the reference's product (0 for tail threads)
-        // round(c * scale) without a conversion instruction: |c * scale| < 2^21, so adding 1.5 * 2^23
-        // leaves the integer in the mantissa
-        const int q = __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000;
-        if (ngroups) {
-#pragma unroll
-          for (int g = 0; g < 3; g++) {
-            if (g < ngroups) {  // warp-uniform
-              const int sum = __reduce_add_sync(0xffffffffu, gid == g ? q : 0);
-              if (lead && gid == g) atomicAdd(cell + t, sum);
-            }
-          }
-        } else {
-          atomicAdd(cell + t, q);
+        for (int t = 0; t < CT; t++) {
+          const int sum = __reduce_add_sync(0xffffffffu, contribution(k, t));
+          if (lead) atomicAdd(cell + t, sum);
         }
+      }
+    } else if (ngroups == 2) {
+      const bool g0 = gid == 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int *cell = cell_of(k);
+#pragma unroll
+        for (int t = 0; t < CT; t++) {
+          const int q = contribution(k, t);
+          const int s0 = __reduce_add_sync(0xffffffffu, g0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, g0 ? 0 : q);
+          if (lead) atomicAdd(cell + t, g0 ? s0 : s1);
+        }
+      }
+    } else if (ngroups == 3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int *cell = cell_of(k);
+#pragma unroll
+        for (int t = 0; t < CT; t++) {
+          const int q = contribution(k, t);
+          const int s0 = __reduce_add_sync(0xffffffffu, gid == 0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, gid == 1 ? q : 0),
+                    s2 = __reduce_add_sync(0xffffffffu, gid == 2 ? q : 0);
+          if (lead) atomicAdd(cell + t, gid == 0 ? s0 : (gid == 1 ? s1 : s2));
+        }
+      }
+    } else if (ngroups == 4) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int *cell = cell_of(k);
+#pragma unroll
+        for (int t = 0; t < CT; t++) {
+          const int q = contribution(k, t);
+          const int s0 = __reduce_add_sync(0xffffffffu, gid == 0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, gid == 1 ? q : 0),
+                    s2 = __reduce_add_sync(0xffffffffu, gid == 2 ? q : 0), s3 = __reduce_add_sync(0xffffffffu, gid == 3 ? q : 0);
+          if (lead) atomicAdd(cell + t, gid < 2 ? (gid == 0 ? s0 : s1) : (gid == 2 ? s2 : s3));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int *cell = cell_of(k);
+#pragma unroll
+        for (int t = 0; t < CT; t++) atomicAdd(cell + t, contribution(k, t));
       }
     }
   }
