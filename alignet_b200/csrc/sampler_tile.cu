@@ -186,12 +186,18 @@ __global__ void __launch_bounds__(kTileThreads, 5)
       return __float_as_int(__fmaf_rn(c, scale, 12582912.0f)) - 0x4B400000;
     };
     auto cell_of = [&](int k) { return s_gv + t0 + ((k & 1) ? CT : 0) + ((k & 2) ? ty : 0) + ((k & 4) ? tz : 0); };
+    // a channel whose gradOut is zero in the whole warp contributes exact zeros: skipped (the cage up-sample's 4th
+    // channel always is -- the field's 4th component has no gradient, ...c:822)
+    bool live[CT];
+#pragma unroll
+    for (int t = 0; t < CT; t++) live[t] = !ngroups || __any_sync(0xffffffffu, go[t] != 0.f);
     if (ngroups == 1) {
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         int *cell = cell_of(k);
 #pragma unroll
         for (int t = 0; t < CT; t++) {
+          if (!live[t]) continue;
           const int sum = __reduce_add_sync(0xffffffffu, contribution(k, t));
           if (lead) atomicAdd(cell + t, sum);
         }
@@ -203,6 +209,7 @@ __global__ void __launch_bounds__(kTileThreads, 5)
         int *cell = cell_of(k);
 #pragma unroll
         for (int t = 0; t < CT; t++) {
+          if (!live[t]) continue;
           const int q = contribution(k, t);
           const int s0 = __reduce_add_sync(0xffffffffu, g0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, g0 ? 0 : q);
           if (lead) atomicAdd(cell + t, g0 ? s0 : s1);
@@ -214,6 +221,7 @@ __global__ void __launch_bounds__(kTileThreads, 5)
         int *cell = cell_of(k);
 #pragma unroll
         for (int t = 0; t < CT; t++) {
+          if (!live[t]) continue;
           const int q = contribution(k, t);
           const int s0 = __reduce_add_sync(0xffffffffu, gid == 0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, gid == 1 ? q : 0),
                     s2 = __reduce_add_sync(0xffffffffu, gid == 2 ? q : 0);
@@ -226,6 +234,7 @@ __global__ void __launch_bounds__(kTileThreads, 5)
         int *cell = cell_of(k);
 #pragma unroll
         for (int t = 0; t < CT; t++) {
+          if (!live[t]) continue;
           const int q = contribution(k, t);
           const int s0 = __reduce_add_sync(0xffffffffu, gid == 0 ? q : 0), s1 = __reduce_add_sync(0xffffffffu, gid == 1 ? q : 0),
                     s2 = __reduce_add_sync(0xffffffffu, gid == 2 ? q : 0), s3 = __reduce_add_sync(0xffffffffu, gid == 3 ? q : 0);
