@@ -47,6 +47,14 @@ static size_t slice_target_bytes() {
 
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
+static bool ramp_slices() {  // VOLSTN_HOST_RAMP=0 switches the slice ramps off (A/B timing)
+  static const bool v = [] {
+    const char *e = getenv("VOLSTN_HOST_RAMP");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -85,6 +93,23 @@ int64_t slice_batch(int64_t B, size_t bytes_per_sample) {
   const int64_t per_slot = (B + volstn_host_ctx::kSlots - 1) / volstn_host_ctx::kSlots;
   bs = std::min(bs, per_slot);
   return std::max<int64_t>(bs, 1);
+}
+
+// Slice schedule of the sampler calls: sizes ramp up 1, 2, 4, ... to `bs` and down again over the last 2 * bs samples.
+// The forward is bound by its uploads and only its LAST slice's kernel + download stick out (a one-sample slice makes
+// that 20 us instead of 0.15 ms); the backward is bound by its downloads, which can start as soon as the FIRST slice is
+// through (one sample: 0.1 ms instead of 0.5 ms).
+int64_t slice_len(int64_t b0, int64_t B, int64_t bs, int slice) {
+  int64_t nb = bs;
+  const int64_t up = (int64_t)1 << (slice < 30 ? slice : 30);
+  if (up < nb) nb = up;
+  const int64_t rem = B - b0;
+  if (rem <= 2 * bs) {
+    const int64_t half = (rem + 1) / 2;
+    if (half < nb) nb = half;
+  }
+  if (nb < 1) nb = 1;
+  return nb < rem ? nb : rem;
 }
 
 // a contiguous B-slice of a contiguous 5-D host tensor, re-homed at `dev`
@@ -281,8 +306,9 @@ int volstn_b200_host_sampler_forward(volstn_host_ctx *c, int dtype, int G, const
     if ((rc = ensure_keep(c, &c->keep_grid, &c->keep_grid_cap, ng * B))) return rc;
   }
   int slice = 0;
-  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
-    const int64_t nb = std::min(bs, B - b0);
+  int64_t nb = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += nb, slice++) {
+    nb = ramp_slices() ? slice_len(b0, B, bs, slice) : std::min(bs, B - b0);
     const int s = slice % volstn_host_ctx::kSlots;
     if ((rc = ensure_arena(c, s, need))) break;
     char *dv = static_cast<char *>(c->arena[s]);
@@ -354,8 +380,9 @@ int volstn_b200_host_sampler_backward(volstn_host_ctx *c, int dtype, int G, cons
   c->keep_valid = false;  // one forward, one backward
   int rc = VOLSTN_OK;
   int slice = 0;
-  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += bs, slice++) {
-    const int64_t nb = std::min(bs, B - b0);
+  int64_t nb = 0;
+  for (int64_t b0 = 0; b0 < B && rc == VOLSTN_OK; b0 += nb, slice++) {
+    nb = ramp_slices() ? slice_len(b0, B, bs, slice) : std::min(bs, B - b0);
     const int s = slice % volstn_host_ctx::kSlots;
     if ((rc = ensure_arena(c, s, need))) break;
     char *dv = static_cast<char *>(c->arena[s]);
