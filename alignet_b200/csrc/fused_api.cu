@@ -179,6 +179,12 @@ int volstn_b200_affine_sampler_forward(int dtype, const void *T, const volstn_te
   if (out->size[1] < 2 || out->size[2] < 2 || out->size[3] < 2) return VOLSTN_ERR_SHAPE;  // VolumetricGridGenerator.lua:6-8
   if (desc_numel(out) == 0) return VOLSTN_OK;
   if (!T) return VOLSTN_ERR_ARG;
+  if ((flags & VOLSTN_ALGO_MASK) != VOLSTN_ALGO_ROW && vol->data && out->data && vol->size[1] >= 1 && vol->size[2] >= 1 &&
+      vol->size[3] >= 1) {
+    // contiguous tensors: the flat voxel mapping of the packed kernels
+    if ((rc = affine_forward_packed(static_cast<const float *>(T), vol, out, flags, static_cast<cudaStream_t>(cuda_stream))) != -1)
+      return rc;
+  }
   RowArgs a;
   RowPlan p;
   zero_args(a);

@@ -244,6 +244,84 @@ __global__ void __launch_bounds__(kThreads, 4) k_sampler_bwd_pair(const SamplerA
 }
 
 // =============================================================================================
+// grid generator folded into the packed forward (forward only: the loader-side augmentation and the
+// projector of stn3dtorch/test.lua:15-25 have no backward).  Same flat voxel mapping and tiers as k_sampler_fwd_packed;
+// the sampling coordinate is T[b] . (zn, yn, xn, 1) in the operation order of k_gridgen_fwd.  The three axis tables
+// (float)(-1 + k/(n-1)*2) are evaluated in double ON THE HOST (the same correctly rounded IEEE operations as on the
+// device: identical bits) and arrive as kernel parameters; a thread's (z, y, x) -- hence its three table values --
+// are fixed for the whole walk over the samples, so the per-voxel cost over the plain forward is 18 flops against a
+// 16-byte grid load.  128 instructions per voxel-warp against 169 of the row kernel.
+// =============================================================================================
+constexpr int kAffineTab = 768;  // D + H + W table entries that fit the parameter block
+
+struct AffineArgs {
+  SamplerArgs<float> s;
+  const float *T;
+  float tab[kAffineTab];  // zn[oD], yn[oH], xn[oW]
+};
+
+template <int CT>
+__global__ void __launch_bounds__(kThreads) k_affine_fwd_packed(const __grid_constant__ AffineArgs p) {
+  const SamplerArgs<float> &a = p.s;
+  __shared__ float tab[kAffineTab];
+  for (int i = threadIdx.x; i < a.oD + a.oH + a.oW; i += kThreads) tab[i] = p.tab[i];
+  __syncthreads();
+  constexpr int VPT = 2;
+  const int sW = CT, sH = a.iW * CT, sD = a.iH * a.iW * CT;
+  const unsigned n = a.n32;
+  const unsigned j0 = blockIdx.x * (kThreads * VPT) + threadIdx.x;
+  float zn[VPT], yn[VPT], xn[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; v++) {
+    const unsigned j = min(j0 + v * kThreads, n - 1);
+    const unsigned x = j % (unsigned)a.oW, r = j / (unsigned)a.oW, y = r % (unsigned)a.oH, z = r / (unsigned)a.oH;
+    zn[v] = tab[z], yn[v] = tab[a.oD + y], xn[v] = tab[a.oD + a.oH + x];
+  }
+  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
+    const float *vb = opaque(a.vol + (size_t)b * a.vs32);
+    float *ob = opaque(a.out + (size_t)b * n * CT);
+    float t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) t[i] = __ldg(p.T + (size_t)b * 16 + i);
+    VoxelSetup<float> s[VPT];
+    int tier = 2;
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+      float c3[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)  // ((T0*zn + T1*yn) + T2*xn) + T3
+        c3[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[4 * i], zn[v]), __fmul_rn(t[4 * i + 1], yn[v])),
+                                    __fmul_rn(t[4 * i + 2], xn[v])), t[4 * i + 3]);
+      tier = min(tier, s[v].begin(c3[0], c3[1], c3[2], a));
+    }
+    if (__all_sync(0xffffffffu, tier == 2)) {
+#pragma unroll
+      for (int v = 0; v < VPT; v++) s[v].template finish_fast<false>(a, sD, sH, sW);
+#pragma unroll
+      for (int v = 0; v < VPT; v++) {
+        const unsigned j = j0 + v * kThreads;
+        voxel_forward_ct<float, CT, 4, 1>(s[v], vb, sD, sH, ob + (size_t)j * CT, j < n);
+      }
+    } else if (__all_sync(0xffffffffu, tier >= 1)) {
+#pragma unroll
+      for (int v = 0; v < VPT; v++) s[v].template finish_fast<true>(a, sD, sH, sW);
+#pragma unroll
+      for (int v = 0; v < VPT; v++) {
+        const unsigned j = j0 + v * kThreads;
+        voxel_forward_ct<float, CT, 4, 2>(s[v], vb, sD, sH, ob + (size_t)j * CT, j < n);
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPT; v++) {
+        const unsigned j = j0 + v * kThreads;
+        s[v].finish_exact(a);
+        voxel_forward_ct<float, CT, 4, 0>(s[v], vb, sD, sH, ob + (size_t)j * CT, j < n);
+      }
+    }
+  }
+}
+
+// =============================================================================================
 // generic kernels: arbitrary element strides on dims 0..3 of every tensor (the CPU reference
 // honours them, ...c:460-473), any C, float or double, 64-bit offsets.  One thread per voxel.
 // =============================================================================================
@@ -638,6 +716,45 @@ bool planar_ok(const volstn_tensor5 *vol, const volstn_tensor5 *grid, const vols
 }
 
 }  // namespace
+
+// returns -1 when the flat-mapping kernel does not apply (the caller uses the row kernel)
+int affine_forward_packed(const float *T, const volstn_tensor5 *vol, const volstn_tensor5 *out, unsigned flags,
+                          cudaStream_t st) {
+  const int64_t C = vol->size[4];
+  if (C < 1 || C > 4 || !packed_ok(4, vol, {out})) return -1;
+  if (out->size[1] + out->size[2] + out->size[3] > kAffineTab) return -1;
+  AffineArgs p;  // 3 KB on the stack; the launch copies it into the parameter block
+  volstn_tensor5 g = *out;  // shape of the (never materialised) grid
+  g.size[4] = 4;
+  fill_common(p.s, vol, &g, out);
+  p.s.out = static_cast<float *>(out->data);
+  p.s.grid = nullptr;
+  p.T = T;
+  if (flags & VOLSTN_DEBUG_NO_FAST) p.s.fbx = p.s.fby = p.s.fbz = 0, p.s.border_ok = 0;
+  if (flags & VOLSTN_DEBUG_NO_BORDER) p.s.border_ok = 0;
+  int o = 0;
+  for (int ax = 1; ax <= 3; ax++) {
+    const int n = (int)out->size[ax];
+    for (int k = 0; k < n; k++) p.tab[o++] = (float)(-1.0 + (double)k / (double)(n - 1) * 2.0);  // VolumetricGridGenerator.lua:17-19
+  }
+  // long-lived CTAs: a thread's table look-ups and index arithmetic are amortised over the samples it walks
+  const unsigned bx = ctas_per_sample(p.s.n, 2);
+  unsigned by = batch_rows(p.s.B, bx);
+  const int rounds_min = p.s.B < 8 ? p.s.B : 8;  // walk at least eight samples per CTA
+  if ((p.s.B + (int)by - 1) / (int)by < rounds_min) by = (unsigned)((p.s.B + rounds_min - 1) / rounds_min);
+  if (const char *e = getenv("VOLSTN_BY")) {  // tuning only
+    const long long v = atoll(e);
+    if (v >= 1 && v <= p.s.B) by = (unsigned)v;
+  }
+  dim3 grid(bx, by), block(kThreads);
+  switch ((int)C) {
+    case 1: k_affine_fwd_packed<1><<<grid, block, 0, st>>>(p); break;
+    case 2: k_affine_fwd_packed<2><<<grid, block, 0, st>>>(p); break;
+    case 3: k_affine_fwd_packed<3><<<grid, block, 0, st>>>(p); break;
+    default: k_affine_fwd_packed<4><<<grid, block, 0, st>>>(p); break;
+  }
+  return after_launch();
+}
 
 int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const volstn_tensor5 *grid,
                          const volstn_tensor5 *out, unsigned flags, cudaStream_t st) {

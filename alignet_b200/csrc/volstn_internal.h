@@ -53,6 +53,10 @@ int row_sampler_backward(int G, const volstn_tensor5 *vol, const volstn_tensor5 
                          const volstn_tensor5 *gradGrid, const volstn_tensor5 *gradOut, bool only_grid, bool only_vol,
                          unsigned flags, cudaStream_t st);
 
+// grid generator folded into the PACKED forward (sampler.cu); -1 when it does not apply
+int affine_forward_packed(const float *T, const volstn_tensor5 *vol, const volstn_tensor5 *out, unsigned flags,
+                          cudaStream_t st);
+
 inline int64_t desc_numel(const volstn_tensor5 *t) {
   return t->size[0] * t->size[1] * t->size[2] * t->size[3] * t->size[4];
 }

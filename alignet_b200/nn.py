@@ -485,11 +485,12 @@ class AffineSamplerVolumetric(Module):
     Values are bit-identical to the two-module chain of this package (gradT: same deterministic reduction
     design, compared within 1e-5 relative)."""
 
-    def __init__(self, depth: int, height: int, width: int, layout: str = "BDHWC", onlyGrid: bool = False):
+    def __init__(self, depth: int, height: int, width: int, layout: str = "BDHWC", onlyGrid: bool = False, algo: int = 0):
         super().__init__()
         assert depth > 1 and height > 1 and width > 1  # VolumetricGridGenerator.lua:6-8
         assert layout in ("BDHWC", "BCDHW")
         self.depth, self.height, self.width, self.layout, self.onlyGrid = depth, height, width, layout, onlyGrid
+        self.algo = algo  # _abi.ALGO_ROW forces the row kernel in the forward (A/B timing)
         self.gradInput = []
 
     def _T(self, T):
@@ -509,7 +510,8 @@ class AffineSamplerVolumetric(Module):
             _require_device(vol.device.index)
             with torch.cuda.device(vol.device):
                 rc = _abi.lib().volstn_b200_affine_sampler_forward(_dtype_code(vol), T.data_ptr(), _desc(v),
-                                                                   _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+                                                                   _desc(_vol_view(out, self.layout)), self.algo & 0xF00,
+                                                                   _stream(vol))
         else:  # host tensors (the loader-side augmentation of dataset_2d.lua:285-311): staged through the GPU
             assert self.layout == "BDHWC", "host tensors: channels-last only"
             rc = _abi.lib().volstn_b200_host_affine_sampler_forward(_host_ctx(), _dtype_code(vol), T.data_ptr(), _desc(v),

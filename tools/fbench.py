@@ -81,6 +81,8 @@ def main():
         f_fus = timed(lambda: fus.updateOutput([vol, T]))
         report("affine chain fwd: gridgen + sampler", f_gen + f_s, 40 * V, f"({f_gen:.1f} + {f_s:.1f})")
         report("affine FUSED fwd", f_fus, 8 * V, f"x{(f_gen + f_s) / f_fus:.2f}")
+        fus_row = vnn.AffineSamplerVolumetric(N, N, N, algo=_abi.ALGO_ROW)
+        report("affine FUSED fwd (row kernel)", timed(lambda: fus_row.updateOutput([vol, T])), 8 * V)
         _, gg = smp.updateGradInput([vol, grid], go)
         b_s = timed(lambda: smp.updateGradInput([vol, grid], go)); b_gen = timed(lambda: gen.updateGradInput(T, gg))
         b_fus = timed(lambda: fus.updateGradInput([vol, T], go))
