@@ -515,8 +515,11 @@ struct CageAcc {
   }
 };
 
-template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false>
-__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC == ROW_SRC_CAGE && !OG) || SRC == ROW_SRC_AFFINE))
+// HEAVY: the 80-register build of the cage kernels that skip the gradVol scatter (OG).  At 64^3 with an 8^3 cage the
+// 64-register build is 2 % faster (365 vs 373 us); with rows of more than 64 voxels (two trips per row) or more than
+// 32 (cell, channel) items per row it spills: 615 vs 355 us at 128^3 x 8, 606 vs 547 us with a 12^3 cage.  The launcher picks.
+template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false, bool HEAVY = false>
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC == ROW_SRC_CAGE && (!OG || HEAVY)) || SRC == ROW_SRC_AFFINE))
     k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];
@@ -744,10 +747,13 @@ int launch_fwd(const RowArgs &a, int B, cudaStream_t st) {
   return VOLSTN_OK;
 }
 
-template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV, bool LOSS = false>
+template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV, bool LOSS = false, bool HEAVY = false>
 int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
+  if constexpr (SRC == ROW_SRC_CAGE && OG && C1 && !HEAVY) {
+    if (a.s.oW > 64 || 3 * (a.cW + 1) > 32) return launch_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, true>(a, B, st);
+  }
   const size_t smem = row_smem_bytes<SRC, true>(a, TWO);
-  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS>, smem);
+  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY>, smem);
   if (rc) return rc;
   for (int b0 = 0; b0 < B; b0 += 65535) {
     RowArgs c = a;
@@ -764,7 +770,7 @@ int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
     if (c.s.out) c.s.out += (long long)b0 * a.oB;
     if (c.loss) c.loss += b0;
     if (c.iou) c.iou += 2 * (long long)b0;
-    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
+    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
     if ((rc = after_launch())) return rc;
   }
   return VOLSTN_OK;

@@ -740,8 +740,10 @@ int affine_forward_packed(const float *T, const volstn_tensor5 *vol, const volst
   // long-lived CTAs: a thread's table look-ups and index arithmetic are amortised over the samples it walks
   const unsigned bx = ctas_per_sample(p.s.n, 2);
   unsigned by = batch_rows(p.s.B, bx);
-  const int rounds_min = p.s.B < 8 ? p.s.B : 8;  // walk at least eight samples per CTA
-  if ((p.s.B + (int)by - 1) / (int)by < rounds_min) by = (unsigned)((p.s.B + rounds_min - 1) / rounds_min);
+  // walk up to eight samples per CTA, as long as about 2 K CTAs remain (32^3 x 32 has 64 CTAs per sample: one sample each)
+  int rounds = p.s.B < 8 ? p.s.B : 8;
+  while (rounds > 1 && (long long)bx * ((p.s.B + rounds - 1) / rounds) < 2048) rounds--;
+  if ((p.s.B + (int)by - 1) / (int)by < rounds) by = (unsigned)((p.s.B + rounds - 1) / rounds);
   if (const char *e = getenv("VOLSTN_BY")) {  // tuning only
     const long long v = atoll(e);
     if (v >= 1 && v <= p.s.B) by = (unsigned)v;
