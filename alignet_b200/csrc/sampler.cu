@@ -130,7 +130,15 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
 #pragma unroll
         for (int v = 0; v < VPT; v++) {
           const unsigned j = j0 + v * kThreads;
-          if (a.quad)
+          // a.quad: 1 = forced (VOLSTN_ALGO_QUAD), 2 = chosen per warp (VOLSTN_ALGO_AUTO): the aligned 16-byte reductions
+          // when the warp's 32 corner-0 cells span 48 elements or more, i.e. when its scalar reductions would not coalesce
+          // anyway.  Identity-like fields never qualify (span <= 33: 187.4 vs 187.3 us); jittered cage 488 -> 467 us,
+          // rotations 508 -> 471 us, uniformly random 867 -> 682 us.  (Testing for exactly consecutive cells instead sent
+          // the identity field to the quad path -- its coordinates sit one ulp below an integer 36 % of the time: 245 us.)
+          bool quad = a.quad == 1;
+          if (a.quad == 2)
+            quad = __reduce_max_sync(0xffffffffu, s[v].fbase) - __reduce_min_sync(0xffffffffu, s[v].fbase) >= 48;
+          if (quad)
             voxel_backward_ct<real, CR, G, ONLY_GRID, ONLY_VOL, 1, true>(a, s[v], vb, gv_delta, sD, sH, go[v],
                                                                          ggb + (size_t)j * GS, j < n);
           else
@@ -840,6 +848,9 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     if (!force_row && packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
       a.quad = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_QUAD && !og && a.C == 1 && a.iW % 4 == 0 &&
                 reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0) ? 1 : 0;
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_AUTO && !og && a.C == 1 && a.iW % 4 == 0 &&
+          reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0)
+        a.quad = 2;
       a.tile_agg = a.n >= 128LL * a.iD * a.iH * a.iW;
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
         return launch_bwd_tile(a, G, ov, st);

@@ -33,7 +33,8 @@ struct SamplerArgs {
   unsigned n32, vs32;
   int border_ok;  // 0 disables the border tier (VOLSTN_DEBUG_NO_BORDER, A/B timing only)
   float one;      // 1.0f, opaque to the optimiser (sampler_pair.cuh::P2)
-  int quad;       // backward fast tier, C = 1: 16-byte vector reductions on aligned quads (VOLSTN_ALGO_QUAD)
+  int quad;       // backward fast tier, C = 1: 16-byte vector reductions on aligned quads: 1 = always (VOLSTN_ALGO_QUAD),
+                  // 2 = per warp, when its cells are scattered (VOLSTN_ALGO_AUTO)
   int no_pair;    // host only: use the scalar VPT = 2 kernels instead of the FADD2/FMUL2 pair kernels
   int tile_agg;   // privatised backward: warp-aggregate the shared atomics (volume much smaller than the output)
   // generic kernels only: element stride of the LAST dimension (channels / grid components) of every tensor.

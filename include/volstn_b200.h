@@ -83,7 +83,8 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_ALGO_AUTO 0x000u
 #define VOLSTN_ALGO_DIRECT 0x100u /* one red.global per in-bounds corner (vector red for C = 2, 4)   */
 #define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA */
-#define VOLSTN_ALGO_QUAD 0x400u   /* backward, C = 1: x0/x0+1 contributions as one 16-byte reduction on the aligned quad */
+#define VOLSTN_ALGO_QUAD 0x400u   /* backward, C = 1: x0/x0+1 contributions as one 16-byte reduction on the aligned quad (AUTO
+                                     chooses this per warp when the warp's cells are scattered; DIRECT never does) */
 #define VOLSTN_ALGO_ROW 0x500u    /* the row kernels (a warp per output row; the path of strided / planar tensors) even for packed tensors */
 #define VOLSTN_ALGO_PAIR 0x300u   /* direct kernels with packed fp32x2 arithmetic (measured slower; kept for A/B) */
 /* debugging / A-B timing: force the slower but always-valid code paths (results are identical) */
