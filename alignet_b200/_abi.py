@@ -20,6 +20,7 @@ BWD_ONLY_VOLUME = 0x2
 BWD_ZERO_GRADVOL = 0x4
 HOST_KEEP_INPUTS = 0x8
 HOST_REUSE_INPUTS = 0x10
+HOST_ASYNC = 0x20
 ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR, ALGO_QUAD, ALGO_ROW = 0x000, 0x100, 0x200, 0x300, 0x400, 0x500
 VPT_SHIFT = 12
 
@@ -63,6 +64,10 @@ SIGNATURES = {
     "volstn_b200_host_ctx_destroy": (_i, [_vp]),
     "volstn_b200_host_pin": (_i, [_vp, _sz]),
     "volstn_b200_host_unpin": (_i, [_vp]),
+    "volstn_b200_host_ticket": (ctypes.c_uint64, [_vp]),
+    "volstn_b200_host_wait": (_i, [_vp, ctypes.c_uint64]),
+    "volstn_b200_host_numa_node": (_i, [_i]),
+    "volstn_b200_host_bind_thread": (_i, [_i]),
     "volstn_b200_host_sampler_forward": (_i, [_vp, _i, _i, _P5, _P5, _P5, _u]),
     "volstn_b200_host_sampler_backward": (_i, [_vp, _i, _i, _P5, _P5, _P5, _P5, _P5, _u]),
     "volstn_b200_host_gridgen_forward": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i64, _i64]),

@@ -19,7 +19,7 @@ const char *volstn_b200_strerror(int status) {
     case VOLSTN_OK: return "ok";
     case VOLSTN_ERR_ARG: return "invalid argument (null pointer, bad dtype/G/flags, negative size)";
     case VOLSTN_ERR_SHAPE: return "tensor shapes violate the module contract (BilinearSamplerVolumetric.lua:26-42)";
-    case VOLSTN_ERR_LAYOUT: return "unsupported layout (last-dimension stride must be 1; some tensors must be contiguous/aligned)";
+    case VOLSTN_ERR_LAYOUT: return "unsupported layout (a tensor this entry point needs contiguous, dense or non-aliasing is not)";
     case VOLSTN_ERR_CUDA: return "CUDA call failed (see volstn_b200_last_cuda_error_string)";
     case VOLSTN_ERR_UNSUPPORTED: return "unsupported problem size";
     case VOLSTN_ERR_NO_DEVICE: return "no sm_100 (B200) device: this library has no fallback path";

@@ -29,7 +29,7 @@ import torch
 from . import _abi
 from ._abi import Tensor5
 
-__all__ = ["Module", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
+__all__ = ["Module", "host_wait", "host_ticket", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
            "AffineSamplerVolumetric", "CageWarpVolumetric", "CageWarpSmoothL1Volumetric",
            "BilinearSamplerSmoothL1Volumetric"]
 
@@ -84,6 +84,16 @@ def _host_ctx(device: Optional[int] = None) -> ctypes.c_void_p:
     return cache[device]
 
 
+def host_ticket() -> int:
+    """Ticket of the most recent asynchronous host call of this thread (``hostAsync=True`` modules)."""
+    return int(_abi.lib().volstn_b200_host_ticket(_host_ctx()))
+
+
+def host_wait(ticket: int = 0) -> None:
+    """Block until the asynchronous host call with that ticket (0: every call) of this thread is complete."""
+    _abi.check(_abi.lib().volstn_b200_host_wait(_host_ctx(), ticket), "host_wait")
+
+
 def _same_place(*ts: torch.Tensor) -> None:
     dev, dt = ts[0].device, ts[0].dtype
     for t in ts[1:]:
@@ -135,18 +145,23 @@ class BilinearSamplerVolumetric(Module):
                   reference feeds through materialised ``nn.Transpose`` copies around the sampler
                   (stn3dtorch/test.lua:17,21; models/alignet.lua:11,14,21).  The kernels read and write the
                   channel-first tensors in place through permuted views; no copy is made (CUDA tensors only)
-      reuseForwardInputs  host tensors only: updateGradInput re-uses the device copies updateOutput made of
-                  the same (pointer, shape) volume and grid instead of uploading them again -- nn.Module's
-                  contract (backward follows forward on the same input); set False if you mutate the
-                  inputs in place between the two calls
+      reuseForwardInputs  host tensors only, OPT-IN (default False = the reference: updateGradInput reads the tensors
+                  it is given, ...c:587-640): updateGradInput re-uses the device copies updateOutput made of the
+                  same (pointer, shape) volume and grid instead of uploading them again.  Only valid if the inputs
+                  are not modified in place between the two calls -- the library cannot see such a modification
+      hostAsync   host tensors only: both calls return once their copies and kernels are enqueued; the results are
+                  in ``self.output`` / ``self.gradInput`` after ``host_wait()`` (uploads of the next call then
+                  overlap the downloads of this one).  Use pinned tensors, and a module (= a set of output
+                  buffers) per call in flight
     """
 
     def __init__(self, gridWidth: int = 4, onlyGrid: bool = False, onlyVolume: bool = False, algo: int = 0, vpt: int = 0,
-                 reuseForwardInputs: bool = True, layout: str = "BDHWC"):
+                 reuseForwardInputs: bool = False, layout: str = "BDHWC", hostAsync: bool = False):
         super().__init__()
         assert layout in ("BDHWC", "BCDHW")
         self.layout = layout
         self.reuseForwardInputs = reuseForwardInputs
+        self.hostAsync = hostAsync
         self.gradInput = []  # lua:23  self.gradInput = {}
         assert gridWidth in (3, 4)
         self.gridWidth = gridWidth
@@ -245,9 +260,8 @@ class BilinearSamplerVolumetric(Module):
             with torch.cuda.device(inputImages.device):
                 rc = lib.volstn_b200_sampler_forward(dt, self.gridWidth, dv, dg, do, self._flags(), _stream(inputImages))
         else:
-            g = grids if grids.is_contiguous() else grids.contiguous()
-            dg = _desc(g)
-            hf = self._flags() | (_abi.HOST_KEEP_INPUTS if self.reuseForwardInputs else 0)
+            # strided grids are honoured like the reference's CPU code honours them (...c:460-473): no copy
+            hf = self._flags() | (_abi.HOST_KEEP_INPUTS if self.reuseForwardInputs else 0) | (_abi.HOST_ASYNC if self.hostAsync else 0)
             rc = lib.volstn_b200_host_sampler_forward(_host_ctx(), dt, self.gridWidth, dv, dg, do, hf)
         _abi.check(rc, "BilinearSamplerVolumetric_updateOutput")
         self.output = out[0] if _inputImages.dim() == 4 else out
@@ -298,12 +312,12 @@ class BilinearSamplerVolumetric(Module):
                                                       _desc(gradInputImages), _desc(gradGrids), _desc(gradOutput),
                                                       flags, _stream(inputImages))
         else:
-            g = grids if grids.is_contiguous() else grids.contiguous()
-            go = gradOutput if gradOutput.is_contiguous() else gradOutput.contiguous()
             if self.reuseForwardInputs:
                 flags |= _abi.HOST_REUSE_INPUTS
-            rc = lib.volstn_b200_host_sampler_backward(_host_ctx(), dt, self.gridWidth, _desc(inputImages), _desc(g),
-                                                       _desc(gradInputImages), _desc(gradGrids), _desc(go), flags)
+            if self.hostAsync:
+                flags |= _abi.HOST_ASYNC
+            rc = lib.volstn_b200_host_sampler_backward(_host_ctx(), dt, self.gridWidth, _desc(inputImages), _desc(grids),
+                                                       _desc(gradInputImages), _desc(gradGrids), _desc(gradOutput), flags)
         _abi.check(rc, "BilinearSamplerVolumetric_updateGradInput")
         if _gradOutput.dim() == 4:
             self.gradInput = [gradInputImages[0], gradGrids[0]]

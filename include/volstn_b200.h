@@ -45,7 +45,7 @@ typedef enum volstn_status {
   VOLSTN_OK = 0,
   VOLSTN_ERR_ARG = 1,         /* NULL pointer, bad G, bad dtype, negative size                     */
   VOLSTN_ERR_SHAPE = 2,       /* the asserts of BilinearSamplerVolumetric.lua:26-42 do not hold     */
-  VOLSTN_ERR_LAYOUT = 3,      /* last-dimension stride != 1, or volume not contiguous (lua:30)      */
+  VOLSTN_ERR_LAYOUT = 3,      /* a tensor this entry point needs contiguous / dense / non-aliasing is not */
   VOLSTN_ERR_CUDA = 4,        /* a CUDA call failed; see volstn_b200_last_cuda_error()              */
   VOLSTN_ERR_UNSUPPORTED = 5, /* e.g. a sample with >= 2^31 elements                                */
   VOLSTN_ERR_NO_DEVICE = 6,   /* no sm_100 device: the library refuses to run (no fallback)         */
@@ -60,7 +60,8 @@ typedef enum volstn_dtype {
 typedef struct volstn_tensor5 {
   void *data;        /* device pointer (volstn_b200_*) or host pointer (volstn_b200_host_*) */
   int64_t size[5];   /* B, D, H, W, C (volume-like) or G (grid-like)                        */
-  int64_t stride[5]; /* element strides; stride[4] must be 1                                 */
+  int64_t stride[5]; /* element strides, ANY value on all five dimensions (the reference needs
+                        stride[4] == 1, ...c:492-495; this library does not)                 */
 } volstn_tensor5;
 
 /* flags for volstn_b200_sampler_backward ---------------------------------------------------- */
@@ -69,13 +70,17 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_BWD_ZERO_GRADVOL 0x4u  /* zero-fill gradVol inside the call (replaces the Lua :zero() of
                                          BilinearSamplerVolumetric.lua:103); without it gradVol is
                                          ACCUMULATED into, exactly like the reference                       */
-/* HOST entry points only: keep device copies of the forward call's volume and grid in the context
- * (KEEP, forward) and let the next backward call on the SAME host tensors skip their upload (REUSE,
- * backward).  Legal under nn.Module's contract -- updateGradInput(input, gradOutput) presumes
- * updateOutput(input) ran before with the same input -- and worth 320 of the 704 MB a 64^3 x 64 step
- * uploads.  Matched by host pointer, shape, strides and dtype; ignored when they differ. */
+/* HOST entry points only, OPT-IN (the reference's CPU code re-reads its inputs in updateGradInput, ...c:587-640, and
+ * that is what flags = 0 does): keep device copies of the forward call's volume and grid in the context (KEEP,
+ * forward) and let the next backward call on the SAME host tensors skip their upload (REUSE, backward) -- 320 of
+ * the 704 MB a 64^3 x 64 step uploads.  Matched by host pointer, shape, strides and dtype only: the caller promises
+ * not to have modified the tensors between the two calls. */
 #define VOLSTN_HOST_KEEP_INPUTS 0x8u
 #define VOLSTN_HOST_REUSE_INPUTS 0x10u
+/* HOST sampler entry points: return as soon as the copies and kernels are enqueued; the outputs are valid (and the
+ * inputs may be modified again) after volstn_b200_host_wait().  With pinned host memory the uploads of the next call
+ * then overlap the downloads of this one. */
+#define VOLSTN_HOST_ASYNC 0x20u
 /* algorithm selection (bits 8..11), 0 = automatic.  Results are identical up to the summation
  * order of gradVol; exposed so that bench.py / profiles can time each variant. */
 #define VOLSTN_ALGO_SHIFT 8
@@ -220,11 +225,16 @@ int volstn_b200_cumsum_backward(int dtype, const void *gradOut, void *gradIn, in
 
 /* ---------------------------------------------------------------------------------------------
  * HOST-buffer entry points: what `require 'libvolstn'` binds for torch.FloatTensor /
- * torch.DoubleTensor (init.c:13-21).  Pointers in the descriptors are HOST pointers (pinned memory
- * gives full PCIe bandwidth; pageable memory works).  The batch is cut into slices that are
- * pipelined H2D -> kernel -> D2H over several streams; the call returns when the outputs are in
- * host memory.  A context owns the device staging buffers and streams and may be reused across
- * calls from one thread at a time; create one per thread for concurrent use.
+ * torch.DoubleTensor (init.c:13-21; lua/init.c in this repository is that binding).  Pointers in the
+ * descriptors are HOST pointers (pinned memory gives full PCIe bandwidth; pageable memory works).  The
+ * batch is cut into slices that are pipelined H2D -> kernel -> D2H over several streams; the call
+ * returns when the outputs are in host memory (unless VOLSTN_HOST_ASYNC).  A context owns the device
+ * staging buffers and streams and may be reused across calls from one thread at a time; create one per
+ * thread for concurrent use.
+ * Sampler tensors may be strided on every dimension, as the reference's CPU code honours them
+ * (...c:460-473, 607-630): dense slices move with one copy, others with pitched copies over their
+ * contiguous runs (a layout that would need more than 32768 copies per slice is VOLSTN_ERR_LAYOUT, and so
+ * is an OUTPUT tensor whose elements alias each other).  Inputs may be broadcast (stride 0).
  * ------------------------------------------------------------------------------------------- */
 typedef struct volstn_host_ctx volstn_host_ctx;
 
@@ -233,6 +243,15 @@ int volstn_b200_host_ctx_destroy(volstn_host_ctx *ctx);
 /* pin / unpin a caller-owned host buffer (cudaHostRegister); optional, for bandwidth only */
 int volstn_b200_host_pin(void *ptr, size_t bytes);
 int volstn_b200_host_unpin(void *ptr);
+/* asynchronous calls (VOLSTN_HOST_ASYNC): ticket of the most recently enqueued call, and wait until the call with
+ * that ticket (and everything before it) is complete; ticket 0 waits for everything */
+uint64_t volstn_b200_host_ticket(volstn_host_ctx *ctx);
+int volstn_b200_host_wait(volstn_host_ctx *ctx, uint64_t ticket);
+/* NUMA placement of host buffers: memory node next to `device` (-1 if the platform does not say), and pin the
+ * CALLING THREAD to the CPUs next to it so that memory it allocates and first touches afterwards is node-local
+ * (a no-op without topology information) */
+int volstn_b200_host_numa_node(int device);
+int volstn_b200_host_bind_thread(int device);
 
 int volstn_b200_host_sampler_forward(volstn_host_ctx *ctx, int dtype, int G, const volstn_tensor5 *vol,
                                      const volstn_tensor5 *grid, const volstn_tensor5 *out, unsigned flags);
@@ -245,7 +264,9 @@ int volstn_b200_host_gridgen_forward(volstn_host_ctx *ctx, int dtype, const void
 int volstn_b200_host_gridgen_backward(volstn_host_ctx *ctx, int dtype, const void *gradGrid, void *gradT,
                                       int64_t B, int64_t D, int64_t H, int64_t W);
 /* the fused modules on HOST tensors (contiguous, float): see volstn_b200_affine_sampler_* / volstn_b200_cage_warp_*.
- * gradVol is always zero-filled first (the module's :zero()); workspace is owned by the context. */
+ * gradVol is always zero-filled first (the module's :zero()); workspace is owned by the context.  VOLSTN_F64 is
+ * refused with VOLSTN_ERR_UNSUPPORTED: these are new modules, the reference's Double registration (init.c:18-19)
+ * covers the four sampler functions only, and those accept VOLSTN_F64 above. */
 int volstn_b200_host_affine_sampler_forward(volstn_host_ctx *ctx, int dtype, const void *T, const volstn_tensor5 *vol,
                                             const volstn_tensor5 *out, unsigned flags);
 int volstn_b200_host_affine_sampler_backward(volstn_host_ctx *ctx, int dtype, const void *T, const volstn_tensor5 *vol,

@@ -1,0 +1,15 @@
+-- volstn (B200): package loader, same shape as stn3dtorch/init.lua:1-12.
+-- `libvolstn` / `libcuvolstn` are built from lua/init.c / lua/init.cu and link libvolstn_b200.so.
+require 'nn'
+local withCuda = pcall(require, 'cutorch')
+
+require 'libvolstn'
+if withCuda then
+   require 'libcuvolstn'
+end
+
+require('volstn.VolumetricGridGenerator')
+require('volstn.BilinearSamplerVolumetric')
+require('volstn.Cumsum')
+
+return nn

@@ -49,7 +49,7 @@ def _desc(a: np.ndarray) -> _Tensor5:
 
 def build(verbose: bool = False) -> None:
     """Compile the C restatement and, when /root/reference is present, the reference itself."""
-    r = subprocess.run(["make", "-C", HERE, "oracle", "ref", "refcuda"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", HERE, "oracle", "ref", "refcuda", "refinit"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout, r.stderr)
     if r.returncode != 0:
@@ -88,6 +88,12 @@ def ref_lib(dtype):
     return _ref[dtype]
 
 
+def default_impl() -> str:
+    """``ref`` (the reference's own C, compiled unmodified) whenever oracle/_ref is present -- it travels to the
+    GPU box with the snapshot -- else the pinned C restatement."""
+    return "ref" if have_ref() else "port"
+
+
 def _suffix(dtype) -> str:
     return {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}[np.dtype(dtype)]
 
@@ -101,9 +107,11 @@ def _check(vol, grid, G):
 # --------------------------------------------------------------------------------------------
 # sampler: forward / backward / index dump  (impl = "port" | "ref")
 # --------------------------------------------------------------------------------------------
-def sampler_forward(vol: np.ndarray, grid: np.ndarray, G: int = 4, impl: str = "port", out=None) -> np.ndarray:
-    """nn_(BilinearSamplerVolumetric_updateOutput) (G=4, ...c:442) / BilinearSamplerBHWD (G=3, ...c:9)."""
+def sampler_forward(vol: np.ndarray, grid: np.ndarray, G: int = 4, impl: str = None, out=None) -> np.ndarray:
+    """nn_(BilinearSamplerVolumetric_updateOutput) (G=4, ...c:442) / BilinearSamplerBHWD (G=3, ...c:9).
+    impl: "ref" | "port" | None = ``default_impl()``."""
     _check(vol, grid, G)
+    impl = impl or default_impl()
     if out is None:
         out = np.empty(grid.shape[:4] + (vol.shape[4],), vol.dtype)
     tv, tg, to = _desc(vol), _desc(grid), _desc(out)
@@ -118,24 +126,26 @@ def sampler_forward(vol: np.ndarray, grid: np.ndarray, G: int = 4, impl: str = "
     return out
 
 
-def sampler_backward(vol, grid, grad_out, G: int = 4, impl: str = "port", grad_vol=None, only_grid=False):
+def sampler_backward(vol, grid, grad_out, G: int = 4, impl: str = None, grad_vol=None, only_grid=False):
     """nn_(BilinearSamplerVolumetric_updateGradInput) (...c:585) / BHWD twin (...c:169).
 
     Returns (gradVol, gradGrid).  gradVol is zero-filled first, as the Lua wrapper does
     (BilinearSamplerVolumetric.lua:101-104), unless an accumulator is passed in.
     """
     _check(vol, grid, G)
+    impl = impl or default_impl()
     assert grad_out.shape == grid.shape[:4] + (vol.shape[4],)
     if grad_vol is None:
         grad_vol = np.zeros_like(vol)
     grad_grid = np.zeros_like(grid)
-    ts = [_desc(vol), _desc(grid), _desc(grad_vol), _desc(grad_grid), _desc(grad_out)]
+    # the reference never enables onlyGrid (...c:594): with impl="ref" its gradVol goes to a scratch tensor
+    gv_arg = np.zeros_like(vol) if (only_grid and impl != "port") else grad_vol
+    ts = [_desc(vol), _desc(grid), _desc(gv_arg), _desc(grad_grid), _desc(grad_out)]
     if impl == "port":
         fn = getattr(port_lib(), "oracle_sampler_backward_" + _suffix(vol.dtype))
         rc = fn(ctypes.c_int(G), *[ctypes.byref(t) for t in ts], ctypes.c_int(int(only_grid)))
         assert rc == 0
     else:
-        assert not only_grid, "the reference never enables onlyGrid (...c:594)"
         arr = (_Tensor5 * 5)(*ts)
         rc = ref_lib(vol.dtype).ref_call(1 if G == 4 else 3, 5, arr)
         assert rc == 1

@@ -79,10 +79,18 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.volstn_b200_sampler_forward(0, 4, vol, g3, out, 0, None) == _abi.ERR_SHAPE        # lua:34
     bad_out = desc((2, 3, 3, 2, 1))
     assert lib.volstn_b200_sampler_forward(0, 4, vol, grid, bad_out, 0, None) == _abi.ERR_SHAPE  # lua:73
-    # the HOST entry points take contiguous tensors only (the device ones honour any strides)
-    strided = desc((2, 3, 3, 3, 4))
-    strided.stride[4] = 2
-    assert lib.volstn_b200_host_sampler_forward(ctypes.c_void_p(1), 0, 4, vol, strided, out, 0) == _abi.ERR_LAYOUT
+    # the HOST entry points honour strides too (...c:460-473), but an OUTPUT whose elements alias each other, a
+    # negative stride, or a layout too fragmented for DMA copies is refused before the context is touched
+    aliased = desc((2, 3, 3, 3, 1))
+    aliased.stride[3] = 0
+    assert lib.volstn_b200_host_sampler_forward(ctypes.c_void_p(1), 0, 4, vol, grid, aliased, 0) == _abi.ERR_LAYOUT
+    neg = desc((2, 3, 3, 3, 4))
+    neg.stride[2] = -12
+    assert lib.volstn_b200_host_sampler_forward(ctypes.c_void_p(1), 0, 4, vol, neg, out, 0) == _abi.ERR_LAYOUT
+    frag_v, frag_g, frag_o = desc((1, 4, 4, 4, 2)), desc((1, 256, 256, 4, 4)), desc((1, 256, 256, 4, 2))
+    # three irregular levels: runs of 2 elements, pitched over W, and 65536 (z, y) pairs that each need their own copy
+    frag_o.stride[3], frag_o.stride[2], frag_o.stride[1], frag_o.stride[0] = 3, 13, 13 * 256 + 1, (13 * 256 + 1) * 256
+    assert lib.volstn_b200_host_sampler_forward(ctypes.c_void_p(1), 0, 4, frag_v, frag_g, frag_o, 0) == _abi.ERR_LAYOUT
     # fused modules: float only, generator extents > 1, bounded cage, exclusive ONLY_ flags
     o5 = desc((2, 3, 3, 3, 1))
     assert lib.volstn_b200_affine_sampler_forward(1, 1 << 20, vol, o5, 0, None) == _abi.ERR_UNSUPPORTED

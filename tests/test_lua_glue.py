@@ -1,0 +1,99 @@
+"""The drop-in boundary itself (SURVEY 8 b): lua/init.c and lua/init.cu -- the replacements of stn3dtorch/init.c and
+stn3dtorch/init.cu -- compiled against stand-in Torch7 headers and opened through a fake Lua state
+(tests/luat_harness).  No GPU needed here: registration, names, stack discipline, argument checking.  The calls
+themselves are exercised on the GPU in tests/test_gpu_lua_glue.py."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.luat_harness import luat
+
+REF_GENERIC = "/root/reference/stn3dtorch/generic/BilinearSamplerVolumetric.c"
+REF_CU = "/root/reference/stn3dtorch/BilinearSamplerVolumetric.cu"
+
+
+@pytest.fixture(scope="module")
+def built():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_glue", os.path.join(luat.ROOT, "lua", "build_glue.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from alignet_b200 import build as b
+    b.build()
+    return mod.build()
+
+
+def test_luaopen_libvolstn_registers_the_reference_names(built):
+    h = luat.Harness(luat.DROPIN_CPU)
+    assert h.opened == 1                      # `return 1` (the table), init.c:20
+    assert h.global_table() == "volstn"       # init.c:15-17
+    assert h.stack_after_open == 1            # the new table stays, every metatable was popped (...c:840-842)
+    regs = h.registrations()
+    assert all(table == "nn" for _, table, _ in regs)
+    for tname in ("torch.FloatTensor", "torch.DoubleTensor"):   # init.c:18-19
+        names = [n for t, _, n in regs if t == tname]
+        assert names[:4] == luat.REFERENCE_NAMES                 # generic/...c:831-836, same order
+        assert names[4:] == luat.NEW_NAMES
+    assert {t for t, _, _ in regs} == {"torch.FloatTensor", "torch.DoubleTensor"}
+    h.close()
+
+
+def test_luaopen_libcuvolstn_registers_the_reference_names(built):
+    h = luat.Harness(luat.DROPIN_CUDA)
+    assert h.opened == 1 and h.stack_after_open == 1             # init.cu:12-14
+    regs = h.registrations()
+    assert [t for t, _, _ in regs] == ["torch.CudaTensor"] * 8   # ...cu:1083-1088
+    assert [n for _, _, n in regs][:4] == luat.REFERENCE_NAMES   # ...cu:1074-1080 (the OnlyGrid line is commented out there)
+    assert [n for _, _, n in regs][4:] == luat.NEW_NAMES
+    h.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GENERIC), reason="reference sources not present on this box")
+def test_names_match_the_reference_source_text(built):
+    """The literal list in the harness against the reference's registration tables as they stand in its sources."""
+    def table(path):
+        src = open(path).read()
+        body = src[src.rindex("luaL_Reg"):]
+        body = body[:body.index("NULL")]
+        body = "\n".join(l for l in body.splitlines() if not l.strip().startswith("//"))
+        return re.findall(r'\{"(\w+)"', body)
+    assert table(REF_GENERIC) == luat.REFERENCE_NAMES
+    assert sorted(table(REF_CU)) == sorted(luat.REFERENCE_NAMES)   # the .cu lists the BHWD pair first; a table has no order
+
+
+@pytest.mark.skipif(not os.path.exists(luat.REFERENCE_CPU), reason="oracle/_ref/libvolstn_refinit.so not built")
+def test_reference_init_c_registers_the_same_through_the_same_harness(built):
+    """stn3dtorch/init.c itself, compiled unmodified behind the same stand-in headers: same global, same types, same
+    four names -- the drop-in registers a superset."""
+    ref, ours = luat.Harness(luat.REFERENCE_CPU), luat.Harness(luat.DROPIN_CPU)
+    assert ref.opened == ours.opened == 1 and ref.global_table() == ours.global_table() == "volstn"
+    assert ref.stack_after_open == ours.stack_after_open
+    assert set(ref.registrations()) <= set(ours.registrations())
+    assert [n for t, _, n in ref.registrations() if t == "torch.FloatTensor"] == luat.REFERENCE_NAMES
+    ref.close(), ours.close()
+
+
+def test_type_dispatch_and_argument_errors_are_lua_errors(built):
+    h = luat.Harness(luat.DROPIN_CPU)
+    v = np.zeros((1, 2, 2, 2, 1), np.float32)
+    g = np.zeros((1, 2, 2, 2, 4), np.float32)
+    o = np.zeros((1, 2, 2, 2, 1), np.float32)
+    # a Double tensor handed to the Float function: luaT_checkudata raises (generic/...c:444-446)
+    with pytest.raises(luat.LuaError, match="torch.FloatTensor expected"):
+        h.call("BilinearSamplerVolumetric_updateOutput", v, g.astype(np.float64), o)
+    with pytest.raises(luat.LuaError, match="expected, got nil"):
+        h.call("BilinearSamplerVolumetric_updateOutput", v, g)
+    with pytest.raises(luat.LuaError, match="5-D tensor expected"):
+        h.call("BilinearSamplerVolumetric_updateOutput", v[0], g, o)
+    with pytest.raises(luat.LuaError, match="nil value"):
+        h.call("BilinearSamplerVolumetric_updateGradInputOnlyGrid", v, g, o)   # commented out in the reference too
+    # module-contract violations come back as the reference's `printf + THError("aborting")` (...cu:736-740)
+    with pytest.raises(luat.LuaError, match="aborting"):
+        h.call("BilinearSamplerVolumetric_updateOutput", v, np.zeros((2, 2, 2, 2, 4), np.float32), o)   # batch mismatch, lua:33
+    with pytest.raises(luat.LuaError, match="bx4x4"):
+        h.call("VolumetricGridGenerator_updateOutput", np.zeros((2, 3, 4), np.float32), np.zeros((2, 2, 2, 2, 4), np.float32))
+    with pytest.raises(luat.LuaError, match="B x N x d1"):
+        h.call("Cumsum_updateOutput", np.zeros((2, 2, 4, 4, 4), np.float32), np.zeros((2, 2, 4, 4, 4), np.float32))
+    h.close()
