@@ -21,7 +21,8 @@ BWD_ZERO_GRADVOL = 0x4
 HOST_KEEP_INPUTS = 0x8
 HOST_REUSE_INPUTS = 0x10
 HOST_ASYNC = 0x20
-ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_PAIR, ALGO_QUAD, ALGO_ROW = 0x000, 0x100, 0x200, 0x300, 0x400, 0x500
+FAST_ARITH = 0x40000
+ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_QUAD, ALGO_ROW = 0x000, 0x100, 0x200, 0x400, 0x500
 VPT_SHIFT = 12
 
 

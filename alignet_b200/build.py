@@ -23,7 +23,7 @@ LIB = os.path.join(CSRC, "libvolstn_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "rowwarp.cu", "fused_api.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
-HEADERS = ["volstn_common.cuh", "sampler.cuh", "sampler_pair.cuh", "rowwarp.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
+HEADERS = ["volstn_common.cuh", "sampler.cuh", "rowwarp.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -56,16 +56,25 @@ def up_to_date() -> bool:
     return os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """``defines`` / ``out``: a tuning VARIANT of the library (e.g. ("VOLSTN_BWD_CTAS=5",) ->
+    csrc/variants/libvolstn_b200_ctas5.so) for the sweep scripts under tools/ (they load it through VOLSTN_B200_LIB)."""
+    if out is not None:
+        return _build(list(defines), out, os.path.join(BUILD, "variant_" + os.path.basename(out).replace(".so", "")), verbose)
     if not force and up_to_date():
         return LIB
+    return _build([], LIB, BUILD, verbose)
+
+
+def _build(defines, LIB, BUILD, verbose):
     nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
     def compile_one(src: str):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
@@ -95,5 +104,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="build a tuning variant with this macro")
+    ap.add_argument("--out", default=None, help="path of the variant library")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.defines, a.out))

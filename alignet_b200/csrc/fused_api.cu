@@ -71,8 +71,6 @@ bool plan_volume(RowArgs &a, RowPlan &p, const volstn_tensor5 *vol, const volstn
   const unsigned sW = p.c1 ? 1u : (unsigned)a.vW;
   s.fneg = (int)(0u - 0x4B000000u * ((unsigned)a.vD + (unsigned)a.vH + sW));
   s.border_ok = 1;
-  s.one = 1.0f;
-  s.no_pair = 1;
   return true;
 }
 
@@ -275,6 +273,7 @@ int volstn_b200_cage_warp_forward(int dtype, const void *cage, const int64_t cag
   a.s.out = static_cast<float *>(out->data);
   a.cage = static_cast<const float *>(cage);
   a.cD = (int)cage_dims[0], a.cH = (int)cage_dims[1], a.cW = (int)cage_dims[2];
+  p.fast = (flags & VOLSTN_FAST_ARITH) ? 1 : 0;
   plan_debug_flags(a, flags);
   plan_geometry(a, p);
   return row_forward(a, p, a.s.B, static_cast<cudaStream_t>(cuda_stream));
@@ -314,6 +313,7 @@ int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t ca
   a.cage = static_cast<const float *>(cage);
   a.gcage = static_cast<float *>(gradCage);
   a.cD = (int)cage_dims[0], a.cH = (int)cage_dims[1], a.cW = (int)cage_dims[2];
+  p.fast = (flags & VOLSTN_FAST_ARITH) ? 1 : 0;
   plan_debug_flags(a, flags);
   plan_geometry(a, p);
   return row_backward(a, p, a.s.B, og, ov, st);
@@ -369,6 +369,7 @@ int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_d
   a.loss_norm = grad_scale;
   a.loss = loss_sum;
   a.iou = reinterpret_cast<unsigned long long *>(iou_counts);
+  p.fast = (flags & VOLSTN_FAST_ARITH) ? 1 : 0;
   plan_debug_flags(a, flags);
   plan_geometry(a, p);
   return row_cage_step(a, p, a.s.B, og, st);

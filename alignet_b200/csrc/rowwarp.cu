@@ -49,6 +49,8 @@ struct RowSmem {
   float *gc;     // CAGE backward: gradient of the cage, same cells x 3
   int *xs;       // CAGE backward: xs[t] = first x whose low cage cell is >= t  (t = 0 .. cW)
   float *stage;  // CAGE backward: per warp, per slot: 6 x oWp products (wx * gg[c], (1 - wx) * gg[c])
+  float *nodes;  // CAGE, fast arithmetic: per warp, per row of the trip: cW + 2 (z, y) pairs, then cW + 2 x values (cage_nodes)
+  int4 *nitem;   // CAGE, fast arithmetic: the (node, component) item lane `i` (and i + 32) computes for every row
 };
 
 __host__ __device__ inline int row_cells(const RowArgs &a) { return (a.cD + 1) * (a.cH + 1) * (a.cW + 1); }
@@ -61,7 +63,7 @@ __host__ __device__ inline size_t row_smem_bytes(const RowArgs &a, bool two_rows
   const size_t axes = (size_t)a.s.oD + a.s.oH + a.s.oW;
   if (SRC == ROW_SRC_AFFINE) return axes * 4;
   if (SRC == ROW_SRC_CAGE) {
-    size_t n = (size_t)row_cells(a) * 16 + axes * 8;
+    size_t n = (size_t)row_cells(a) * 16 + axes * 8 + 8 + 64 * 16 + (size_t)kRowWarps * 2 * (a.cW + 2) * 12;
     if (BWD) n += (size_t)row_cells(a) * 12 + (size_t)(a.cW + 2) * 4 + (size_t)kRowWarps * (two_rows ? 2 : 1) * 6 * row_owp(a) * 4;
     return n;
   }
@@ -85,8 +87,10 @@ __device__ __forceinline__ void row_carve(RowSmem &m, unsigned char *raw, const 
     m.iz = reinterpret_cast<int *>(m.tx + oW);
     m.iy = m.iz + oD;
     m.ix = m.iy + oH;
+    m.nitem = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(m.ix + oW) + ((oD + oH + oW) & 1) * 8);  // 16-byte aligned
+    m.nodes = reinterpret_cast<float *>(m.nitem + 64);
     if constexpr (BWD) {
-      m.gc = reinterpret_cast<float *>(m.ix + oW);
+      m.gc = m.nodes + kRowWarps * 2 * 3 * (a.cW + 2);
       m.xs = reinterpret_cast<int *>(m.gc + 3 * row_cells(a));
       m.stage = reinterpret_cast<float *>(m.xs + a.cW + 2);
     }
@@ -141,6 +145,15 @@ __device__ __forceinline__ void row_fill(const RowSmem &m, const RowArgs &a, int
       m.tz[i] = w;  // tz / ty / tx and iz / iy / ix are consecutive
       m.iz[i] = i0;
     }
+    // fast arithmetic: item i = (component c, x-node t) of a row's node vector; where its four cage values live in the
+    // cage's shared-memory copy viewed as floats ((z, y) pairs first, then the x plane) and where the node goes
+    if (threadIdx.x < 64) {
+      const int cWp = a.cW + 1, it = threadIdx.x;
+      const int c = it / cWp, t = it - c * cWp;
+      int4 e = make_int4(-1, 0, 0, 0);
+      if (c < 3) e = c < 2 ? make_int4(t, c, 2, 2 * t + c) : make_int4(t, 2 * row_cells(a), 1, 2 * (a.cW + 2) + t);
+      m.nitem[it] = e;
+    }
     if constexpr (BWD) {
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -193,6 +206,49 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
   zf = az, yf = ay, xf = ax;
 }
 
+// ---- fast arithmetic (VOLSTN_FAST_ARITH) ------------------------------------------------------------------------
+// Along an output row (z, y fixed) the up-sampled field is piecewise LINEAR in x: inside cage x-cell t it is
+//   wx * N[t] + (1 - wx) * N[t + 1],     N[t] = sum over the row's four (y, z) cage corners of (wy' * wz') * cage[.., .., t]
+// so the eight 12-byte corner loads and 24 multiplies per voxel of cage_field() become, per ROW, one node vector N
+// (cW + 1 nodes x 3 components, one (node, component) item per lane) and, per VOXEL, two node loads and three lerps.
+// Same mathematics, different rounding: the field agrees with cage_field() to a few ulp (tests: <= 1e-6 absolute on
+// coordinates in [-1, 1]), NOT bit for bit -- hence a flag, off by default.
+// nodes of output row (z, y) into `nbuf` (one row's 3 * (cW + 2) floats of this warp's buffer)
+__device__ __forceinline__ void cage_nodes(const RowSmem &m, const RowArgs &a, float *nbuf, int z, int y, int lane) {
+  const int cWp = a.cW + 1, cHWp = (a.cH + 1) * cWp;
+  const float wy = m.ty[y], wz = m.tz[z];
+  const float wy1 = 1.0f - wy, wz1 = 1.0f - wz;
+  const float w00 = wy * wz, w10 = wy1 * wz, w01 = wy * wz1, w11 = wy1 * wz1;  // (y', z')
+  const int cbase = (m.iz[z] * (a.cH + 1) + m.iy[y]) * cWp;
+  const float *cf = reinterpret_cast<const float *>(m.cgzy);
+  const int items = 3 * cWp;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (lane + 32 * i < items) {
+      const int4 e = m.nitem[lane + 32 * i];  // (t, source base, source stride, destination)
+      const float *p = cf + e.y + (cbase + e.x) * e.z;
+      const int sy = cWp * e.z, sz = cHWp * e.z;
+      float v = w00 * p[0];
+      v = fmaf(w10, p[sy], v);
+      v = fmaf(w01, p[sz], v);
+      v = fmaf(w11, p[sz + sy], v);
+      nbuf[e.w] = v;
+    }
+  }
+}
+__device__ __forceinline__ void cage_field_sep(const RowSmem &m, const float *nbuf, int nstride, int x, float &zf, float &yf,
+                                               float &xf) {
+  const float wx = m.tx[x], wx1 = 1.0f - wx;
+  const int i = m.ix[x];
+  const float2 *nzy = reinterpret_cast<const float2 *>(nbuf);
+  const float *nx = nbuf + 2 * nstride;
+  const float2 a0 = nzy[i], a1 = nzy[i + 1];
+  const float b0 = nx[i], b1 = nx[i + 1];
+  zf = fmaf(wx, a0.x, wx1 * a1.x);
+  yf = fmaf(wx, a0.y, wx1 * a1.y);
+  xf = fmaf(wx, b0, wx1 * b1);
+}
+
 // The same with the lane's eight cage corners kept in registers (compile with -DROW_CAGE_CACHE=1): a lane's x (hence
 // its cage column) is the same for every row of a one-trip kernel and the row's cage cell (z0, y0) changes only
 // every few rows, so the eight 16-byte shared-memory loads (4 wavefronts each: the L1/LSU pipe is what bounds the
@@ -236,11 +292,37 @@ __device__ __forceinline__ void cage_field_cached(const RowSmem &m, const RowArg
   zf = az, yf = ay, xf = ax;
 }
 
-template <int SRC, bool AOS4>
+template <int SRC, bool AOS4, bool FASTM = false>
 struct RowCoords {
   // per-CTA state of the source
   float t[12];
   const float *gb;
+  // fast arithmetic: this warp's node buffer (two rows of 3 * (cW + 2) floats)
+  float *nbuf;
+  int nstride, nlane;
+  __device__ __forceinline__ void init_nodes(const RowSmem &m, const RowArgs &a, int wid, int lane) {
+    if constexpr (SRC == ROW_SRC_CAGE && FASTM) {
+      nstride = a.cW + 2;
+      nbuf = m.nodes + wid * 2 * 3 * nstride;
+      nlane = lane;
+    }
+  }
+  // the nodes of the trip's rows: (z, y) and, for a two-row trip, the next row.  Bracketed by __syncwarp(): the lanes
+  // that wrote a node are not the ones that read it.
+  template <bool TWO_ROWS>
+  __device__ __forceinline__ void row_begin(const RowSmem &m, const RowArgs &a, int z, int y, bool second_row) {
+    if constexpr (SRC == ROW_SRC_CAGE && FASTM) {
+      __syncwarp();
+      cage_nodes(m, a, nbuf, z, y, nlane);
+      if constexpr (TWO_ROWS) {
+        if (second_row) {
+          const bool wrap = y + 1 == a.s.oH;
+          cage_nodes(m, a, nbuf + 3 * nstride, wrap ? z + 1 : z, wrap ? 0 : y + 1, nlane);
+        }
+      }
+      __syncwarp();
+    }
+  }
   CageCorners cc[(SRC == ROW_SRC_CAGE && ROW_CAGE_CACHE) ? 2 : 1];
   __device__ __forceinline__ void init(const RowArgs &a, int b) {
     if constexpr (SRC == ROW_SRC_AFFINE) {
@@ -266,6 +348,9 @@ struct RowCoords {
       zf = affine_row(t, 0, zn, yn, xn);
       yf = affine_row(t, 1, zn, yn, xn);
       xf = affine_row(t, 2, zn, yn, xn);
+    } else if constexpr (FASTM) {
+      // V = slot of the trip: with two rows per trip slot 1 is the second row (clamped to the first at the end)
+      cage_field_sep(m, nbuf + ((V && second_slot_row) ? 3 * nstride : 0), nstride, x, zf, yf, xf);
     } else {
       if constexpr (ROW_CAGE_CACHE)
         cage_field_cached(m, a, z, y, x, cc[V], zf, yf, xf);
@@ -273,6 +358,7 @@ struct RowCoords {
         cage_field(m, a, z, y, x, zf, yf, xf);
     }
   }
+  bool second_slot_row = false;  // set per trip by the kernels (TWO_ROWS and the second row exists)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -290,7 +376,39 @@ __device__ __forceinline__ float sum8(const float (&cw)[8], const float (&v)[8])
   return acc;
 }
 
-template <bool C1, int MODE>
+// fast arithmetic: the same eight terms as one FMA chain
+__device__ __forceinline__ float sum8_fma(const float (&cw)[8], const float (&v)[8]) {
+  float acc = cw[0] * v[0];
+#pragma unroll
+  for (int k = 1; k < 8; k++) acc = fmaf(cw[k], v[k], acc);
+  return acc;
+}
+
+// fast arithmetic: gradGrid factored per axis -- d/dx = sum over the four (y', z') of (wy' wz') (dot[x+1] - dot[x]) etc. --
+// 12 weight products, 12 differences, 12 FMAs instead of the reference's 40 products and 21 sums (...c:792-817)
+__device__ __forceinline__ void grad_grid_fast(const float (&dot)[8], const VoxelSetup<float> &s, const SamplerArgs<float> &a,
+                                               float &gz, float &gy, float &gx) {
+  const float wx1 = 1.0f - s.wx, wy1 = 1.0f - s.wy, wz1 = 1.0f - s.wz;
+  // corner k: x = k & 1, y = (k >> 1) & 1, z = k >> 2
+  const float yz[4] = {s.wy * s.wz, wy1 * s.wz, s.wy * wz1, wy1 * wz1};  // index y + 2 z
+  const float xz[4] = {s.wx * s.wz, wx1 * s.wz, s.wx * wz1, wx1 * wz1};  // index x + 2 z
+  const float xy[4] = {s.wx * s.wy, wx1 * s.wy, s.wx * wy1, wx1 * wy1};  // index x + 2 y
+  float dx = yz[0] * (dot[1] - dot[0]);
+  dx = fmaf(yz[1], dot[3] - dot[2], dx);
+  dx = fmaf(yz[2], dot[5] - dot[4], dx);
+  dx = fmaf(yz[3], dot[7] - dot[6], dx);
+  float dy = xz[0] * (dot[2] - dot[0]);
+  dy = fmaf(xz[1], dot[3] - dot[1], dy);
+  dy = fmaf(xz[2], dot[6] - dot[4], dy);
+  dy = fmaf(xz[3], dot[7] - dot[5], dy);
+  float dz = xy[0] * (dot[4] - dot[0]);
+  dz = fmaf(xy[1], dot[5] - dot[1], dz);
+  dz = fmaf(xy[2], dot[6] - dot[2], dz);
+  dz = fmaf(xy[3], dot[7] - dot[3], dz);
+  gz = dz * (a.dm1 * 0.5f), gy = dy * (a.hm1 * 0.5f), gx = dx * (a.wm1 * 0.5f);
+}
+
+template <bool C1, int MODE, bool FASTM = false>
 __device__ __forceinline__ void row_voxel_forward(const RowArgs &a, const VoxelSetup<float> &s, const float *__restrict__ vb,
                                                   float *__restrict__ o, bool valid) {
   constexpr bool FAST = MODE == 1;
@@ -304,7 +422,7 @@ __device__ __forceinline__ void row_voxel_forward(const RowArgs &a, const VoxelS
 #pragma unroll
     for (int k = 0; k < 8; k++)
       v[k] = (FAST || s.in(k)) ? __ldg(rows.p[k >> 1] + ((k & 1) ? sW : 0) + (C1 ? 0 : t * a.vC)) : 0.f;
-    const float r = a.g3 ? sum8<1>(cw, v) : sum8<0>(cw, v);
+    const float r = FASTM ? sum8_fma(cw, v) : (a.g3 ? sum8<1>(cw, v) : sum8<0>(cw, v));
     if (valid) st_stream_f1(o + (C1 ? 0 : t * a.osC), r);
   }
 }
@@ -313,11 +431,12 @@ __device__ __forceinline__ void row_voxel_forward(const RowArgs &a, const VoxelS
 // LOSS (single channel, fused training step): `gop` points at the TARGET voxel; the forward value is formed from the
 // gathers that the backward needs anyway, gradOut is the SmoothL1 gradient norm * clamp(out - target, -1, 1)
 // (THNN SmoothL1Criterion_updateGradInput) and (out, target) are handed back for the loss / IoU accumulators.
-template <bool C1, bool OG, bool OV, int MODE, bool LOSS = false>
+template <bool C1, bool OG, bool OV, int MODE, bool LOSS = false, bool FASTM = false>
 __device__ __forceinline__ void row_voxel_backward(const RowArgs &a, const VoxelSetup<float> &s, const float *__restrict__ vb,
                                                    long long gv_delta, const float *__restrict__ gop, bool valid,
                                                    float &gz, float &gy, float &gx, float *fwd = nullptr,
                                                    float *tgt = nullptr) {
+  static_assert(!FASTM || C1, "fast arithmetic: single-channel cage kernels only");
   static_assert(!LOSS || (C1 && !OV), "the fused step is single-channel and needs the gathers");
   constexpr bool FAST = MODE == 1;
   const int sW = C1 ? 1 : a.vW;
@@ -336,14 +455,15 @@ __device__ __forceinline__ void row_voxel_backward(const RowArgs &a, const Voxel
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = (FAST || s.in(k)) ? __ldg(rows.p[k >> 1] + ((k & 1) ? sW : 0) + co) : 0.f;
       if constexpr (LOSS) {
-        const float o = a.g3 ? sum8<1>(cw, v) : sum8<0>(cw, v);  // the forward value, bit for bit (...c:566-573 / 149-156)
+        // the forward value: bit for bit (...c:566-573 / 149-156), or one FMA chain with fast arithmetic
+        const float o = FASTM ? sum8_fma(cw, v) : (a.g3 ? sum8<1>(cw, v) : sum8<0>(cw, v));
         const float x = __fsub_rn(o, go);
         *fwd = o, *tgt = go;
         go = x < -1.0f ? -a.loss_norm : (x > 1.0f ? a.loss_norm : __fmul_rn(a.loss_norm, x));
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        const float d = __fadd_rn(dot[k], __fmul_rn(v[k], go));  // dot += v * go (...c:736)
+        const float d = FASTM ? v[k] * go : __fadd_rn(dot[k], __fmul_rn(v[k], go));  // dot += v * go (...c:736)
         dot[k] = (FAST || s.in(k)) ? d : dot[k];                 // an out-of-bounds corner never sees go
       }
     }
@@ -354,7 +474,12 @@ __device__ __forceinline__ void row_voxel_backward(const RowArgs &a, const Voxel
           red_add(const_cast<float *>(rows.p[k >> 1]) + ((k & 1) ? sW : 0) + co + gv_delta, __fmul_rn(cw[k], go));  // ...c:737
     }
   }
-  if constexpr (!OV) grad_grid_from_dots<float>(dot, s, a.s, gz, gy, gx);
+  if constexpr (!OV) {
+    if constexpr (FASTM)
+      grad_grid_fast(dot, s, a.s, gz, gy, gx);
+    else
+      grad_grid_from_dots<float>(dot, s, a.s, gz, gy, gx);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -391,6 +516,10 @@ __device__ __forceinline__ void row_advance(int &z, int &y, int step, int oH) {
 #ifndef ROW_MIN_CTAS
 #define ROW_MIN_CTAS 0
 #endif
+// fast-arithmetic cage backward kernels: 1 = the 80-register build (3 resident CTAs), 0 = 64 registers (4 CTAs)
+#ifndef ROW_FAST_HEAVY
+#define ROW_FAST_HEAVY 1
+#endif
 #ifndef ROW_MIN_CTAS_HEAVY
 #define ROW_MIN_CTAS_HEAVY 3
 #endif
@@ -403,7 +532,7 @@ constexpr int row_min_ctas(int src, bool bwd, bool c1, bool heavy = false) {
   return (src == ROW_SRC_GRID && !bwd) ? 5 : 4;
 }
 
-template <int SRC, bool AOS4, bool C1, bool TWO_ROWS>
+template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool FASTM = false>
 __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_row_fwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SamplerArgs<float> &s = a.s;
@@ -413,8 +542,9 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_r
   row_carve<SRC, false>(m, smem_raw, a);
   row_fill<SRC, false>(m, a, b);
   if constexpr (SRC != ROW_SRC_GRID) __syncthreads();
-  RowCoords<SRC, AOS4> src;
+  RowCoords<SRC, AOS4, FASTM> src;
   src.init(a, b);
+  src.init_nodes(m, a, wid, lane);
   const float *vb = opaque(s.vol + (long long)b * a.vB);
   float *ob = opaque(s.out + (long long)b * a.oB);
   const int sW = C1 ? 1 : a.vW;
@@ -422,6 +552,8 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_r
   const int r_end = min(r + a.rows_per_warp, s.oD * s.oH);
   int z = r / s.oH, y = r - z * s.oH;
   for (; r < r_end; r += TWO_ROWS ? 2 : 1, row_advance(z, y, TWO_ROWS ? 2 : 1, s.oH)) {
+    src.second_slot_row = TWO_ROWS && r + 1 < r_end;
+    src.template row_begin<TWO_ROWS>(m, a, z, y, src.second_slot_row);
     for (int xb = 0; xb < s.oW; xb += TWO_ROWS ? 32 : 64) {
       RowSlot sl[2];
       row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
@@ -441,17 +573,17 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, false, C1)) k_r
 #pragma unroll
         for (int v = 0; v < 2; v++) su[v].template finish_fast<false>(s, a.vD, a.vH, sW);
 #pragma unroll
-        for (int v = 0; v < 2; v++) row_voxel_forward<C1, 1>(a, su[v], vb, o[v], sl[v].valid);
+        for (int v = 0; v < 2; v++) row_voxel_forward<C1, 1, FASTM>(a, su[v], vb, o[v], sl[v].valid);
       } else if (__all_sync(0xffffffffu, tier >= 1)) {
 #pragma unroll
         for (int v = 0; v < 2; v++) su[v].template finish_fast<true>(s, a.vD, a.vH, sW);
 #pragma unroll
-        for (int v = 0; v < 2; v++) row_voxel_forward<C1, 2>(a, su[v], vb, o[v], sl[v].valid);
+        for (int v = 0; v < 2; v++) row_voxel_forward<C1, 2, FASTM>(a, su[v], vb, o[v], sl[v].valid);
       } else {
 #pragma unroll
         for (int v = 0; v < 2; v++) {
           su[v].finish_exact(s);
-          row_voxel_forward<C1, 0>(a, su[v], vb, o[v], sl[v].valid);
+          row_voxel_forward<C1, 0, FASTM>(a, su[v], vb, o[v], sl[v].valid);
         }
       }
     }
@@ -518,8 +650,8 @@ struct CageAcc {
 // HEAVY: the 80-register build of the cage kernels that skip the gradVol scatter (OG).  At 64^3 with an 8^3 cage the
 // 64-register build is 2 % faster (365 vs 373 us); with rows of more than 64 voxels (two trips per row) or more than
 // 32 (cell, channel) items per row it spills: 615 vs 355 us at 128^3 x 8, 606 vs 547 us with a 12^3 cage.  The launcher picks.
-template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false, bool HEAVY = false>
-__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC == ROW_SRC_CAGE && (!OG || HEAVY)) || SRC == ROW_SRC_AFFINE))
+template <int SRC, bool AOS4, bool C1, bool TWO_ROWS, bool OG, bool OV, bool LOSS = false, bool HEAVY = false, bool FASTM = false>
+__global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC == ROW_SRC_CAGE && (!OG || HEAVY || (FASTM && ROW_FAST_HEAVY))) || SRC == ROW_SRC_AFFINE))
     k_row_bwd(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[kRowWarps][12];
@@ -530,8 +662,9 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC 
   row_carve<SRC, true>(m, smem_raw, a);
   row_fill<SRC, true>(m, a, b);
   if constexpr (SRC != ROW_SRC_GRID) __syncthreads();
-  RowCoords<SRC, AOS4> src;
+  RowCoords<SRC, AOS4, FASTM> src;
   src.init(a, b);
+  src.init_nodes(m, a, wid, lane);
   const float *vb = opaque(s.vol + (long long)b * a.vB);
   const long long gv_delta = s.gvol - s.vol;  // gradVol has the volume's strides
   const float *gob = opaque(s.gout + (long long)b * a.oB);
@@ -555,6 +688,8 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC 
   const int r_end = min(r + a.rows_per_warp, s.oD * s.oH);
   int z = r / s.oH, y = r - z * s.oH;
   for (; r < r_end; r += TWO_ROWS ? 2 : 1, row_advance(z, y, TWO_ROWS ? 2 : 1, s.oH)) {
+    src.second_slot_row = TWO_ROWS && r + 1 < r_end;
+    src.template row_begin<TWO_ROWS>(m, a, z, y, src.second_slot_row);
     for (int xb = 0; xb < s.oW; xb += TWO_ROWS ? 32 : 64) {
       RowSlot sl[2];
       row_slots<TWO_ROWS>(sl, r, r_end, z, y, xb, lane, s.oH, s.oW);
@@ -576,18 +711,18 @@ __global__ void __launch_bounds__(kRowThreads, row_min_ctas(SRC, true, C1, (SRC 
         for (int v = 0; v < 2; v++) su[v].template finish_fast<false>(s, a.vD, a.vH, sW);
 #pragma unroll
         for (int v = 0; v < 2; v++)
-          row_voxel_backward<C1, OG, OV, 1, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
+          row_voxel_backward<C1, OG, OV, 1, LOSS, FASTM>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
       } else if (__all_sync(0xffffffffu, tier >= 1)) {
 #pragma unroll
         for (int v = 0; v < 2; v++) su[v].template finish_fast<true>(s, a.vD, a.vH, sW);
 #pragma unroll
         for (int v = 0; v < 2; v++)
-          row_voxel_backward<C1, OG, OV, 2, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
+          row_voxel_backward<C1, OG, OV, 2, LOSS, FASTM>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
       } else {
 #pragma unroll
         for (int v = 0; v < 2; v++) {
           su[v].finish_exact(s);
-          row_voxel_backward<C1, OG, OV, 0, LOSS>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
+          row_voxel_backward<C1, OG, OV, 0, LOSS, FASTM>(a, su[v], vb, gv_delta, gop[v], sl[v].valid, gz[v], gy[v], gx[v], &fo[v], &ft[v]);
         }
       }
       if constexpr (LOSS) {
@@ -728,10 +863,10 @@ int set_smem(K kernel, size_t bytes) {
   return VOLSTN_OK;
 }
 
-template <int SRC, bool AOS4, bool C1, bool TWO>
+template <int SRC, bool AOS4, bool C1, bool TWO, bool FASTM = false>
 int launch_fwd(const RowArgs &a, int B, cudaStream_t st) {
   const size_t smem = row_smem_bytes<SRC, false>(a, TWO);
-  int rc = set_smem(k_row_fwd<SRC, AOS4, C1, TWO>, smem);
+  int rc = set_smem(k_row_fwd<SRC, AOS4, C1, TWO, FASTM>, smem);
   if (rc) return rc;
   for (int b0 = 0; b0 < B; b0 += 65535) {
     RowArgs c = a;
@@ -741,19 +876,19 @@ int launch_fwd(const RowArgs &a, int B, cudaStream_t st) {
     if (c.s.grid) c.s.grid += (long long)b0 * a.gB;
     if (c.T) c.T += (long long)b0 * 16;
     if (c.cage) c.cage += (long long)b0 * 3 * a.cD * a.cH * a.cW;
-    k_row_fwd<SRC, AOS4, C1, TWO><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
+    k_row_fwd<SRC, AOS4, C1, TWO, FASTM><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
     if ((rc = after_launch())) return rc;
   }
   return VOLSTN_OK;
 }
 
-template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV, bool LOSS = false, bool HEAVY = false>
+template <int SRC, bool AOS4, bool C1, bool TWO, bool OG, bool OV, bool LOSS = false, bool HEAVY = false, bool FASTM = false>
 int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
   if constexpr (SRC == ROW_SRC_CAGE && OG && C1 && !HEAVY) {
-    if (a.s.oW > 64 || 3 * (a.cW + 1) > 32) return launch_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, true>(a, B, st);
+    if (a.s.oW > 64 || 3 * (a.cW + 1) > 32) return launch_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, true, FASTM>(a, B, st);
   }
   const size_t smem = row_smem_bytes<SRC, true>(a, TWO);
-  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY>, smem);
+  int rc = set_smem(k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY, FASTM>, smem);
   if (rc) return rc;
   for (int b0 = 0; b0 < B; b0 += 65535) {
     RowArgs c = a;
@@ -770,7 +905,7 @@ int launch_bwd(const RowArgs &a, int B, cudaStream_t st) {
     if (c.s.out) c.s.out += (long long)b0 * a.oB;
     if (c.loss) c.loss += b0;
     if (c.iou) c.iou += 2 * (long long)b0;
-    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
+    k_row_bwd<SRC, AOS4, C1, TWO, OG, OV, LOSS, HEAVY, FASTM><<<dim3(a.nblk, nb), kRowThreads, smem, st>>>(c);
     if ((rc = after_launch())) return rc;
   }
   return VOLSTN_OK;
@@ -826,7 +961,11 @@ int row_forward(const RowArgs &a, const RowPlan &p, int B, cudaStream_t st) {
   switch (p.src) {
     case ROW_SRC_GRID: return p.grid_aos4 ? fwd_pick<ROW_SRC_GRID, true>(a, p, B, st) : fwd_pick<ROW_SRC_GRID, false>(a, p, B, st);
     case ROW_SRC_AFFINE: return fwd_pick<ROW_SRC_AFFINE, false>(a, p, B, st);
-    default: return fwd_pick<ROW_SRC_CAGE, false>(a, p, B, st);
+    default:
+      if (p.fast && p.c1)
+        return p.two_rows ? launch_fwd<ROW_SRC_CAGE, false, true, true, true>(a, B, st)
+                          : launch_fwd<ROW_SRC_CAGE, false, true, false, true>(a, B, st);
+      return fwd_pick<ROW_SRC_CAGE, false>(a, p, B, st);
   }
 }
 
@@ -842,7 +981,15 @@ int row_backward(const RowArgs &a, const RowPlan &p, int B, bool og, bool ov, cu
         return after_launch();
       }
       return VOLSTN_OK;
-    default: return bwd_mode<ROW_SRC_CAGE, false>(a, p, B, og, ov, st);
+    default:
+      if (p.fast && p.c1 && !ov) {
+        if (og)
+          return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, true, false, false, false, true>(a, B, st)
+                            : launch_bwd<ROW_SRC_CAGE, false, true, false, true, false, false, false, true>(a, B, st);
+        return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, false, false, false, false, true>(a, B, st)
+                          : launch_bwd<ROW_SRC_CAGE, false, true, false, false, false, false, false, true>(a, B, st);
+      }
+      return bwd_mode<ROW_SRC_CAGE, false>(a, p, B, og, ov, st);
   }
 }
 
@@ -864,6 +1011,13 @@ int row_cage_step(const RowArgs &a, const RowPlan &p, int B, bool og, cudaStream
                       : launch_bwd<ROW_SRC_GRID, false, true, false, false, false, true>(a, B, st);
   }
   if (p.src != ROW_SRC_CAGE) return VOLSTN_ERR_UNSUPPORTED;
+  if (p.fast) {
+    if (og)
+      return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, true, false, true, false, true>(a, B, st)
+                        : launch_bwd<ROW_SRC_CAGE, false, true, false, true, false, true, false, true>(a, B, st);
+    return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, false, false, true, false, true>(a, B, st)
+                      : launch_bwd<ROW_SRC_CAGE, false, true, false, false, false, true, false, true>(a, B, st);
+  }
   if (og)
     return p.two_rows ? launch_bwd<ROW_SRC_CAGE, false, true, true, true, false, true>(a, B, st)
                       : launch_bwd<ROW_SRC_CAGE, false, true, false, true, false, true>(a, B, st);

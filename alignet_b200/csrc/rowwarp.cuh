@@ -50,6 +50,7 @@ struct RowPlan {
   int grid_aos4;  // ROW_SRC_GRID: grid (and gradGrid) are `... x 4` with unit component stride, 16-byte aligned
   int c1;         // single channel (compile-time body); otherwise the runtime channel loop
   int two_rows;   // oW <= 32: a warp trip covers two rows
+  int fast;       // ROW_SRC_CAGE, single channel: VOLSTN_FAST_ARITH (separable cage up-sample, FMA sums, factored gradGrid)
 };
 
 // CTAs per sample and rows per warp for `rows` = oD * oH output rows (deterministic: the workspace query and the

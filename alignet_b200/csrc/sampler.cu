@@ -14,7 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "sampler_pair.cuh"
+#include "sampler.cuh"
 #include "volstn_internal.h"
 
 namespace volstn {
@@ -95,8 +95,14 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
   }
 }
 
+// resident CTAs per SM the single-channel float backward is compiled for (register cap 65536 / (256 * n)): 6 -> 40
+// registers, 5 -> 48, 4 -> 64.  Swept again in round 2 with the per-warp quad path in the body
+// (profiles/r02_bwd_launch_bounds.md).
+#ifndef VOLSTN_BWD_CTAS
+#define VOLSTN_BWD_CTAS 6
+#endif
 template <typename real, int CT, int G, int VPT, bool ONLY_GRID, bool ONLY_VOL>
-__global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 : 1) k_sampler_bwd_packed(const SamplerArgs<real> a) {
+__global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? VOLSTN_BWD_CTAS : 1) k_sampler_bwd_packed(const SamplerArgs<real> a) {
   const int C = CT ? CT : a.C;
   constexpr int CR = CT ? CT : 1;
   const int sW = C, sH = a.iW * C, sD = a.iH * a.iW * C;
@@ -173,80 +179,6 @@ __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? 6 :
           voxel_backward_packed<real, CT, G, ONLY_GRID, ONLY_VOL>(a, s, vb, gvb, sD, sH, sW, gob + (size_t)j * C,
                                                                   ggb + (size_t)j * GS);
       }
-    }
-  }
-}
-
-// =============================================================================================
-// pair kernels (float, C <= 4; opt-in, VOLSTN_ALGO_PAIR): the VPT = 2 packed kernels with the arithmetic
-// of both voxels of a thread done in packed fp32x2 instructions (sampler_pair.cuh).  Same launch
-// geometry, same tiers, bit-identical results -- and 12-25 % SLOWER on a B200 than the scalar kernels
-// (gpurun_out/r1_kbench_pair*.txt): FMUL2 / FFMA2 halve the issue slots of the arithmetic but not its
-// FMA-pipe cycles, and the pairs cost registers (48 / 64 against 32 / 40).  Kept as the measured record.
-// =============================================================================================
-template <int CT, int G>
-__global__ void __launch_bounds__(kThreads, 6) k_sampler_fwd_pair(const SamplerArgs<float> a) {
-  const int sH = a.iW * CT, sD = a.iH * a.iW * CT;
-  const unsigned n = a.n32;
-  const unsigned j0 = blockIdx.x * (kThreads * 2) + threadIdx.x, j1 = j0 + kThreads;
-  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
-    const size_t sb = (size_t)b * n;
-    const float *vb = opaque(a.vol + (size_t)b * a.vs32);
-    const float *gb = opaque(a.grid + sb * G);
-    float *ob = opaque(a.out + sb * CT);
-    f2 zf, yf, xf;
-    ld_grid<float, G>(gb + (size_t)min(j0, n - 1) * G, zf.x, yf.x, xf.x);
-    ld_grid<float, G>(gb + (size_t)min(j1, n - 1) * G, zf.y, yf.y, xf.y);
-    PairSetup s;
-    const int tier = s.begin(zf, yf, xf, a);
-    float *o0 = ob + (size_t)j0 * CT, *o1 = ob + (size_t)j1 * CT;
-    if (__all_sync(0xffffffffu, tier == 2)) {
-      s.finish<1>(a, sD, sH, CT);
-      pair_forward<CT, G, 1>(a, s, vb, sD, sH, o0, o1, j0 < n, j1 < n);
-    } else if (__all_sync(0xffffffffu, tier >= 1)) {
-      s.finish<2>(a, sD, sH, CT);
-      pair_forward<CT, G, 2>(a, s, vb, sD, sH, o0, o1, j0 < n, j1 < n);
-    } else {
-      s.finish<0>(a, sD, sH, CT);
-      pair_forward<CT, G, 0>(a, s, vb, sD, sH, o0, o1, j0 < n, j1 < n);
-    }
-  }
-}
-
-template <int CT, int G, bool ONLY_GRID, bool ONLY_VOL>
-__global__ void __launch_bounds__(kThreads, 4) k_sampler_bwd_pair(const SamplerArgs<float> a) {
-  const int sH = a.iW * CT, sD = a.iH * a.iW * CT;
-  const unsigned n = a.n32;
-  const unsigned j0 = blockIdx.x * (kThreads * 2) + threadIdx.x, j1 = j0 + kThreads;
-  const long long gv_delta = a.gvol - a.vol;  // gradVol is packed like the volume
-  for (unsigned b = blockIdx.y; b < (unsigned)a.B; b += gridDim.y) {
-    const size_t sb = (size_t)b * n;
-    const float *vb = opaque(a.vol + (size_t)b * a.vs32);
-    const float *gb = opaque(a.grid + sb * G);
-    float *ggb = opaque(a.ggrid + sb * G);
-    const float *gob = opaque(a.gout + sb * CT);
-    const size_t c0 = min(j0, n - 1), c1 = min(j1, n - 1);
-    f2 zf, yf, xf;
-    ld_grid<float, G>(gb + c0 * G, zf.x, yf.x, xf.x);
-    ld_grid<float, G>(gb + c1 * G, zf.y, yf.y, xf.y);
-    float g0[CT], g1[CT];
-    ld_channels_stream<float, CT>(gob + c0 * CT, g0);
-    ld_channels_stream<float, CT>(gob + c1 * CT, g1);
-    f2 go[CT];
-#pragma unroll
-    for (int t = 0; t < CT; t++) go[t] = make_float2(g0[t], g1[t]);
-    PairSetup s;
-    const int tier = s.begin(zf, yf, xf, a);
-    float *gg0 = ggb + (size_t)j0 * G, *gg1 = ggb + (size_t)j1 * G;
-    if (__all_sync(0xffffffffu, tier == 2)) {
-      s.finish<1>(a, sD, sH, CT);
-      pair_backward<CT, G, ONLY_GRID, ONLY_VOL, 1>(a, s, vb, gv_delta, sD, sH, go, gg0, gg1, j0 < n, j1 < n);
-    } else if (__all_sync(0xffffffffu, tier >= 1)) {
-      s.finish<2>(a, sD, sH, CT);
-      pair_backward<CT, G, ONLY_GRID, ONLY_VOL, 2>(a, s, vb, gv_delta, sD, sH, go, gg0, gg1, j0 < n, j1 < n);
-    } else {
-      s.finish<0>(a, sD, sH, CT);
-      pair_backward<CT, G, ONLY_GRID, ONLY_VOL, 0>(a, s, vb, gv_delta, sD, sH, go, gg0, gg1, j0 < n, j1 < n);
     }
   }
 }
@@ -494,10 +426,8 @@ void fill_fast(SamplerArgs<real> &a) {
   a.fbx = a.fby = a.fbz = 0;
   a.fneg = 0;
   a.border_ok = 0;
-  a.no_pair = 1;
   a.quad = 0;
   a.tile_agg = 0;
-  a.one = 1.0f;
   if constexpr (sizeof(real) == 4) {
     if (a.iD <= (1 << 22) && a.iH <= (1 << 22) && a.iW <= (1 << 22)) {
       memcpy(&a.fbx, &a.wm1, 4);
@@ -593,15 +523,7 @@ int launch_fwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
     case 4: k_sampler_fwd_packed<float, CT, G, 4><<<dim3(blocks_x(4), by), block, 0, st>>>(a); break;
-    case 2:
-      if constexpr (CT > 0 && G < 10) {
-        if (!a.no_pair) {
-          k_sampler_fwd_pair<CT, G><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
-          break;
-        }
-      }
-      k_sampler_fwd_packed<float, CT, G, 2><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
-      break;
+    case 2: k_sampler_fwd_packed<float, CT, G, 2><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
     default: k_sampler_fwd_packed<float, CT, G, 1><<<dim3(blocks_x(1), by), block, 0, st>>>(a); break;
   }
   return after_launch();
@@ -635,15 +557,7 @@ int launch_bwd_packed(const SamplerArgs<float> &a, int vpt, cudaStream_t st) {
   const unsigned by = batch_rows(a.B, ctas_per_sample(a.n, vpt));
   auto blocks_x = [&](int v) { return ctas_per_sample(a.n, v); };
   switch (vpt) {
-    case 2:
-      if constexpr (CT > 0 && G < 10) {
-        if (!a.no_pair) {
-          k_sampler_bwd_pair<CT, G, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
-          break;
-        }
-      }
-      k_sampler_bwd_packed<float, CT, G, 2, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a);
-      break;
+    case 2: k_sampler_bwd_packed<float, CT, G, 2, OG, OV><<<dim3(blocks_x(2), by), block, 0, st>>>(a); break;
     default: k_sampler_bwd_packed<float, CT, G, 1, OG, OV><<<dim3(blocks_x(1), by), block, 0, st>>>(a); break;
   }
   return after_launch();
@@ -780,7 +694,6 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     a.out = static_cast<float *>(out->data);
     if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
-    a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
     const bool force_row = (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW;
     if (!force_row && packed_ok(G, vol, {grid, out})) {
       const int vpt = pick_vpt(flags, a.C, a.n);
@@ -843,7 +756,6 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
     }
     if (flags & VOLSTN_DEBUG_NO_FAST) a.fbx = a.fby = a.fbz = 0, a.border_ok = 0;
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
-    a.no_pair = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_PAIR) ? 0 : 1;
     const bool force_row = (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW;
     if (!force_row && packed_ok(G, vol, {grid, gradOut, og ? nullptr : gradVol, ov ? nullptr : gradGrid})) {
       a.quad = ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_QUAD && !og && a.C == 1 && a.iW % 4 == 0 &&

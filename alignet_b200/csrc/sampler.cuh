@@ -32,10 +32,8 @@ struct SamplerArgs {
   // that the per-CTA base pointers are one widening multiply each
   unsigned n32, vs32;
   int border_ok;  // 0 disables the border tier (VOLSTN_DEBUG_NO_BORDER, A/B timing only)
-  float one;      // 1.0f, opaque to the optimiser (sampler_pair.cuh::P2)
   int quad;       // backward fast tier, C = 1: 16-byte vector reductions on aligned quads: 1 = always (VOLSTN_ALGO_QUAD),
                   // 2 = per warp, when its cells are scattered (VOLSTN_ALGO_AUTO)
-  int no_pair;    // host only: use the scalar VPT = 2 kernels instead of the FADD2/FMUL2 pair kernels
   int tile_agg;   // privatised backward: warp-aggregate the shared atomics (volume much smaller than the output)
   // generic kernels only: element stride of the LAST dimension (channels / grid components) of every tensor.
   // The reference assumes 1 (`+ t`, `+ 1`, `+ 2`: ...c:492-495, 556); honouring it lets a B x C x D x H x W

@@ -31,7 +31,7 @@ from ._abi import Tensor5
 
 __all__ = ["Module", "host_wait", "host_ticket", "BilinearSamplerVolumetric", "VolumetricGridGenerator", "Cumsum",
            "AffineSamplerVolumetric", "CageWarpVolumetric", "CageWarpSmoothL1Volumetric",
-           "BilinearSamplerSmoothL1Volumetric"]
+           "BilinearSamplerSmoothL1Volumetric", "computeIOU"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -579,11 +579,17 @@ class CageWarpVolumetric(Module):
     ``onlyGrid=True`` skips gradSource (the source is data behind nn.Identity, models/alignet_2d.lua:23-24)."""
 
     def __init__(self, depth: Optional[int] = None, height: Optional[int] = None, width: Optional[int] = None,
-                 layout: str = "BDHWC", onlyGrid: bool = False):
+                 layout: str = "BDHWC", onlyGrid: bool = False, fastArith: bool = False):
         super().__init__()
         assert layout in ("BDHWC", "BCDHW")
         self.depth, self.height, self.width, self.layout, self.onlyGrid = depth, height, width, layout, onlyGrid
+        # VOLSTN_FAST_ARITH (single-channel volumes): separable cage up-sample, FMA sums, factored gradGrid -- values within
+        # 1e-5 of the reference chain instead of bit-identical (include/volstn_b200.h)
+        self.fastArith = fastArith
         self.gradInput = []
+
+    def _fast(self) -> int:
+        return _abi.FAST_ARITH if self.fastArith else 0
 
     def _out_dims(self, v):
         return (self.depth or v.size(1), self.height or v.size(2), self.width or v.size(3))
@@ -606,11 +612,11 @@ class CageWarpVolumetric(Module):
             _require_device(vol.device.index)
             with torch.cuda.device(vol.device):
                 rc = _abi.lib().volstn_b200_cage_warp_forward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
-                                                              _desc(_vol_view(out, self.layout)), 0, _stream(vol))
+                                                              _desc(_vol_view(out, self.layout)), self._fast(), _stream(vol))
         else:
             assert self.layout == "BDHWC", "host tensors: channels-last only"
             rc = _abi.lib().volstn_b200_host_cage_warp_forward(_host_ctx(), _dtype_code(vol), cage.data_ptr(), dims, _desc(v),
-                                                               _desc(out), 0)
+                                                               _desc(out), self._fast())
         _abi.check(rc, "CageWarpVolumetric_updateOutput")
         self.output = out
         return out
@@ -624,7 +630,7 @@ class CageWarpVolumetric(Module):
         gv = torch.empty_like(vol)
         gcage = torch.empty_like(cage)
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
-        flags = _abi.BWD_ZERO_GRADVOL
+        flags = _abi.BWD_ZERO_GRADVOL | self._fast()
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
             gv.zero_()
@@ -659,9 +665,9 @@ class CageWarpSmoothL1Volumetric(Module):
     the exact ``B x 2`` (intersection, union) counts, ``self.output`` the warped volume if ``keepOutput``.
     Single-channel ``B x D x H x W x 1`` CUDA float volumes."""
 
-    def __init__(self, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False):
+    def __init__(self, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False, fastArith: bool = False):
         super().__init__()
-        self.sizeAverage, self.onlyGrid, self.keepOutput = sizeAverage, onlyGrid, keepOutput
+        self.sizeAverage, self.onlyGrid, self.keepOutput, self.fastArith = sizeAverage, onlyGrid, keepOutput, fastArith
         self.gradInput = []
         self.loss = self.lossPerSample = self.iouCounts = None
 
@@ -684,7 +690,7 @@ class CageWarpSmoothL1Volumetric(Module):
         # THNN: norm = sizeAverage ? 1. / ((real)nElement) : 1.  (double division, stored in `real`)
         norm = float(torch.tensor(1.0 / float(torch.tensor(float(n), dtype=torch.float32)), dtype=torch.float32)) if self.sizeAverage else 1.0
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
-        flags = _abi.BWD_ZERO_GRADVOL
+        flags = _abi.BWD_ZERO_GRADVOL | (_abi.FAST_ARITH if self.fastArith else 0)
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
             gv.zero_()
@@ -702,9 +708,27 @@ class CageWarpSmoothL1Volumetric(Module):
         return self.loss, self.gradInput
 
     def iou(self):
-        """computeIOU (util.lua:118-119): mean over the batch of intersection / union"""
+        """Mean over the batch of PER-SAMPLE intersection / union from the kernel's exact counts.  NOT the number
+        util.lua's computeIOU prints: that function groups elements by flat index modulo B (see ``computeIOU`` below,
+        which reproduces it on a kept output)."""
         c = self.iouCounts.to(torch.float64)
         return (c[:, 0] / c[:, 1]).sum() / c.size(0)
+
+
+def computeIOU(predTarget: torch.Tensor, gtTarget: torch.Tensor) -> torch.Tensor:
+    """``computeIOU(predTarget, gtTarget)`` of util.lua:110-120, operation for operation (plain tensor ops, as in the
+    reference; not a kernel of this library).  Inputs are channel-first ``B x C x ...`` like the reference's; only the
+    first channel is used (lua:113-114).  Note the grouping the Lua code really performs: ``:view(-1, B)`` of a B-major
+    tensor followed by a sum over dim 1 collects, in column c, the elements whose flat index is congruent to c modulo B
+    -- not sample c.  The fused step kernels count per sample instead (``iouCounts`` / ``iou()``), a deliberate
+    deviation documented in DESIGN.md."""
+    B = predTarget.size(0)
+    t = (gtTarget[:, :1] > 0.5).double()
+    et = (predTarget[:, :1] > 0.5).double()
+    t_et_sum = t + et
+    intrsct_v = (t_et_sum == 2).double().contiguous().view(-1, B).sum(0, keepdim=True)
+    un_v = (t_et_sum > 0).double().contiguous().view(-1, B).sum(0, keepdim=True)
+    return (intrsct_v / un_v).sum() / B
 
 
 class BilinearSamplerSmoothL1Volumetric(Module):

@@ -2,18 +2,20 @@
 """bench.py -- sampled voxels/s of nn.BilinearSamplerVolumetric forward + backward at 64^3.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--size 64] [--batch 64] [--channels 1] [--grid g2] [--sweep]
+                    [--size 64] [--batch 64] [--channels 1] [--grid g1] [--sweep] [--config sampler|train|contention]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = updateOutput + updateGradInput of the module (gradVol zero-fill included, as
-BilinearSamplerVolumetric.lua:101-104 does it) over one batch of synthetic voxel volumes and an
-ALIGNet-like warp field.  The batch shards over ranks with no collective (samples are independent);
-per-GPU work is fixed, so scaling is "weak".
+BilinearSamplerVolumetric.lua:101-104 does it) over one batch of synthetic voxel volumes and the warp field a
+random-init ALIGNet emits (`g1`, the identity field; the ALIGNet-like sheared field `g2` is timed in the same run
+and reported as `value_g2`).  The batch shards over ranks with no collective (samples are independent); per-GPU
+work is fixed, so scaling is "weak".
 
 JSON line (rank 0): metric/value = whole-job sampled voxels/s with inputs resident in HBM;
-`e2e` = the same through the HOST-buffer C ABI (pinned host tensors in, host tensors out, copies
-inside the timed region); `roofline` = the dominant kernel (backward) against the measured HBM
-copy bandwidth; `cpu_baseline` = the reference's own C code on this box's host cores.
+`e2e` = the same through the HOST-buffer C ABI exactly as the drop-in Lua module calls it (pinned host tensors in,
+host tensors out, every input re-uploaded by both calls, copies inside the timed region; `e2e.variants` holds the
+opt-in modes); `roofline` = the dominant kernel (backward) against the measured HBM copy bandwidth; `cpu_baseline`
+= the reference's own C code on this box's host cores; `train` / `contention` = BASELINE.json configs 3 and 5.
 `--impl reference` times only that CPU implementation and prints the same line shape.
 """
 from __future__ import annotations
@@ -139,9 +141,11 @@ def cpu_reference_rate(N, C, grid_kind, batch, reps, threads, seed=0):
     grid = synth.grid(grid_kind, batch, N, N, N, rng)
     go = synth.grad_output(batch, N, N, N, C, rng)
     times = []
+    bufs = {}
+    oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads, bufs)   # allocates the outputs once (lua: resize)
     for _ in range(reps):
         t0 = time.perf_counter()
-        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads, bufs)
         times.append(time.perf_counter() - t0)
     best = min(times)
     return batch * N ** 3 / best, statistics.mean(times), ("reference" if impl == "ref" else "port")
@@ -153,7 +157,7 @@ def run_reference_arm(a):
         return  # rank 0 alone runs the CPU arm; the others exit 0 without work
     threads = host_threads()
     N, C = a.size, a.channels
-    batch = min(a.batch, max(threads, 8))  # bounded sample: one 64^3 sample per host thread
+    batch = a.batch  # the whole per-GPU batch of the workload (64 samples of 64^3: ~0.1 s per step on 16 threads)
     from alignet_b200 import synth
     from oracle import oracle
     impl = "ref" if oracle.have_ref() else "port"
@@ -161,20 +165,21 @@ def run_reference_arm(a):
     vol = synth.volume("v2", batch, N, N, N, C, rng)
     grid = synth.grid(a.grid, batch, N, N, N, rng)
     go = synth.grad_output(batch, N, N, N, C, rng)
-    for _ in range(a.warmup):
-        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+    bufs = {}
+    for _ in range(max(a.warmup, 1)):
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads, bufs)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads)
+        oracle.sampler_forward_backward_threaded(vol, grid, go, 4, impl, threads, bufs)
     dt = time.perf_counter() - t0
     value = batch * N ** 3 * a.steps / dt
     kind = "reference" if impl == "ref" else "port"
-    sample = (f"{batch} of {a.batch} samples of the {N}^3 C={C} {a.grid} workload per step, "
+    sample = (f"all {batch} samples of the {N}^3 C={C} {a.grid} workload per step (fwd + zero-fill + bwd), "
               f"batch-sliced over {threads} host threads ({'oracle/_ref = reference C compiled unmodified' if impl == 'ref' else 'oracle C port'}, gcc -O2 -ffp-contract=off)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a),
+            "config": dict(workload_config(a), timed_region="K steps of the reference's C functions on host tensors, wall clock"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -218,6 +223,12 @@ def run_ours(a):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world if distributed else 1
+
+    # pinned host buffers next to this rank's GPU: bind the thread to the GPU's local CPUs while they are allocated
+    # and first touched (a no-op where the platform reports one node); restored before the CPU baseline runs
+    full_affinity = os.sched_getaffinity(0)
+    _abi.lib().volstn_b200_host_bind_thread(local)
+    bound_cpus = len(os.sched_getaffinity(0))
 
     N, C, B = a.size, a.channels, a.batch
     V = B * N ** 3
@@ -332,56 +343,7 @@ def run_ours(a):
         # ---- (3) end to end through the HOST-buffer ABI: pinned host in, host out ----
         e2e = None
         if not a.no_e2e:
-            mh = vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)
-
-            def host_step():
-                o = mh.updateOutput([vol_h, grid_h])
-                g = mh.updateGradInput([vol_h, grid_h], go_h)
-                return float(o.view(-1)[0]) + float(g[1].view(-1)[0])  # results are host tensors already
-
-            e2e_steps = max(3, min(a.steps, 10))
-            for _ in range(2):
-                host_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                host_step()
-            barrier()
-            e2e_s = (time.perf_counter() - t0) / e2e_steps
-            if distributed:
-                e2e_s = shard.max_over_ranks(e2e_s, device="cuda")
-            esz = 4
-            # forward uploads volume + grid; backward re-uses those device copies (nn.Module contract: backward
-            # follows forward on the same input, VOLSTN_HOST_REUSE_INPUTS) and uploads only gradOut
-            h2d = (vol_h.numel() + grid_h.numel()) * esz + go_h.numel() * esz
-            d2h = (go_h.numel() + vol_h.numel() + grid_h.numel()) * esz
-            # the host link itself (pinned 256 MiB copies, one direction at a time): the two calls of a step are
-            # synchronous, so the step cannot beat  upload(volume + grid) + download(gradVolume + gradGrid)
-            link = None
-            try:
-                nlk = 256 << 20
-                hb = torch.empty(nlk, dtype=torch.uint8).pin_memory()
-                db = torch.empty(nlk, dtype=torch.uint8, device="cuda")
-
-                def one_way(up):
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    for _ in range(4):
-                        (db.copy_(hb, non_blocking=True) if up else hb.copy_(db, non_blocking=True))
-                    torch.cuda.synchronize()
-                    return nlk * 4 / (time.perf_counter() - t0) / 1e9
-
-                one_way(True), one_way(False)
-                up_gbs, down_gbs = one_way(True), one_way(False)
-                lb_ms = ((vol_h.numel() + grid_h.numel()) * esz / up_gbs + (vol_h.numel() + grid_h.numel()) * esz / down_gbs) / 1e6
-                link = {"h2d_gbs": up_gbs, "d2h_gbs": down_gbs, "lower_bound_ms_per_step": lb_ms, "frac_of_link_bound": lb_ms / (e2e_s * 1e3),
-                        "note": "forward is bound by uploading volume + grid, backward by downloading gradVolume + gradGrid; the smaller transfers overlap"}
-                del hb, db
-            except Exception as e:  # noqa: BLE001
-                link = {"error": repr(e)[:200]}
-            e2e = {"value": V * n_gpus / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "link": link,
-                   "path": "volstn_b200_host_sampler_forward/backward: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors; backward re-uses the forward call's device copies of volume and grid"}
+            e2e = run_e2e(a, torch, dist, vnn, _abi, shard, vol_h, grid_h, go_h, V, n_gpus, distributed, barrier, local)
     clocks = sampler.summary()
 
     peak, peak_src = measured_peak()
@@ -399,14 +361,15 @@ def run_ours(a):
                          "frac": (fwd_alg + bwd_alg) / (ms_per_step * 1e-3) / 1e9 / peak,
                          "note": "48+20C algorithmic B/voxel over the whole step incl. the gradVol zero-fill"}}
 
+    os.sched_setaffinity(0, full_affinity)
     cpu = None
     if rank == 0 and not a.no_cpu:
         threads = host_threads()
-        sample_b = min(B, max(threads, 8))
-        rate, mean_s, kind = cpu_reference_rate(N, C, a.grid, sample_b, reps=2, threads=threads)
+        sample_b = B
+        rate, mean_s, kind = cpu_reference_rate(N, C, a.grid, sample_b, reps=3, threads=threads)
         one_rate, _, _ = cpu_reference_rate(N, C, a.grid, min(B, 4), reps=1, threads=1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"{sample_b} of {B} samples of the same {N}^3 workload, fwd+bwd, batch-sliced over {threads} host threads, best of 2",
+               "sample": f"all {sample_b} samples of the same {N}^3 workload, fwd + zero-fill of both gradInputs + bwd into pre-allocated outputs, batch-sliced over {threads} host threads, best of 3",
                "single_core_value": one_rate}
 
     sweep = run_sweep(a, torch, vnn, synth, _abi) if (a.sweep and rank == 0) else None
@@ -421,20 +384,22 @@ def run_ours(a):
     aux = guarded(run_aux) if (rank == 0 and n_gpus == 1 and not a.no_aux) else None
     fused = guarded(run_fused) if (rank == 0 and n_gpus == 1 and not a.no_aux) else None
 
-    # the same step on the other warp-field families (rank 0, inputs resident, context for the headline)
+    # the same step on the other warp-field families (every rank, inputs resident, max over ranks): `g2`, the sheared
+    # field a TRAINED ALIGNet emits, is the second headline (`value_g2`)
     fields = None
-    if rank == 0 and not a.no_fields:
+    if not a.no_fields:
         fields = {}
         peak_, _ = measured_peak()
         for gk in ("g1", "g2", "g3"):
             if gk == a.grid:
                 continue
-            rng2 = np.random.default_rng(7)
+            rng2 = np.random.default_rng(7 + rank)
             nb = min(B, 8)
             g2 = torch.from_numpy(synth.grid(gk, nb, N, N, N, rng2)).cuda().repeat((B + nb - 1) // nb, 1, 1, 1, 1)[:B].contiguous()
             m2 = vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)
             for _ in range(3):
                 m2.updateOutput([vol, g2]); m2.updateGradInput([vol, g2], go)
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
             e0.record()
@@ -442,9 +407,21 @@ def run_ours(a):
                 m2.updateOutput([vol, g2]); m2.updateGradInput([vol, g2], go)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            fields[gk] = {"desc": GRID_DESC[gk], "ms_per_step": ms, "voxels_per_s": V / (ms * 1e-3),
+            if distributed:
+                ms = shard.max_over_ranks(ms, device="cuda")
+            fields[gk] = {"desc": GRID_DESC[gk], "ms_per_step": ms, "voxels_per_s": V * n_gpus / (ms * 1e-3),
                           "step_frac_of_hbm_peak": (fwd_alg + bwd_alg) / (ms * 1e-3) / 1e9 / peak_}
             del g2
+
+    # BASELINE.json configs 3 and 5 (every rank takes part: config 3 has the path's one collective)
+    extras = {}
+    if not a.no_extra:
+        for name, fn in (("train", run_train_config), ("contention", run_contention_config)):
+            try:
+                extras[name] = fn(a, torch, dist, rank, n_gpus, distributed)
+            except Exception as e:  # noqa: BLE001  (context sections must never cost the contract line)
+                torch.cuda.synchronize()
+                extras[name] = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -455,6 +432,11 @@ def run_ours(a):
                                          if graph is not None else "K steps launched from Python")
         if fields is not None:
             line["other_fields"] = fields
+            if "g2" in fields:
+                line["value_g2"] = fields["g2"]["voxels_per_s"]
+                line["value_g2_note"] = "the same step on the ALIGNet-like sheared field g2 (what a trained network emits), whole job, device-timed"
+        line["config"]["host_buffers"] = f"pinned; thread bound to {bound_cpus} of {len(full_affinity)} CPUs next to the GPU while allocating (volstn_b200_host_bind_thread)"
+        line.update(extras)
         if aux is not None:
             line["aux_kernels"] = aux
         if fused is not None:
@@ -465,6 +447,128 @@ def run_ours(a):
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_e2e(a, torch, dist, vnn, _abi, shard, vol_h, grid_h, go_h, V, n_gpus, distributed, barrier, local):
+    """The step through the HOST-buffer ABI, wall clock, copies inside the timed region, every step's result read on the
+    host.  Headline = the calls lua/BilinearSamplerVolumetric.lua makes (synchronous; every input re-uploaded by both calls
+    like the reference re-reads them, ...c:587-640; the gradVol zero-fill travels as a flag).  `variants`: the unmodified
+    reference Lua file (flags = 0: host-side :zero() of both gradInputs, gradVol uploaded and accumulated into), and the
+    opt-in modes (input reuse, asynchronous calls with two steps in flight)."""
+    lib, d, esz = _abi.lib(), vnn._desc, 4
+    nv, ng, no = vol_h.numel() * esz, grid_h.numel() * esz, go_h.numel() * esz
+    e2e_steps = max(3, min(a.steps, 10))
+
+    def timed_loop(step_fn, finish=None):
+        for _ in range(2):
+            step_fn(0)
+        if finish:
+            finish()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step_fn(i)
+        if finish:
+            finish()
+        barrier()
+        sec = (time.perf_counter() - t0) / e2e_steps
+        return shard.max_over_ranks(sec, device="cuda") if distributed else sec
+
+    def sync_step(m):
+        def f(i):
+            o = m.updateOutput([vol_h, grid_h])
+            g = m.updateGradInput([vol_h, grid_h], go_h)
+            return float(o.view(-1)[0]) + float(g[1].view(-1)[0])  # results are host tensors already
+        return f
+
+    # headline: module defaults = the drop-in Lua module
+    sec = timed_loop(sync_step(vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt)))
+    variants = {}
+    # the reference's UNMODIFIED Lua file over the drop-in library: zero both gradInputs on the host, flags = 0
+    ctx = vnn._host_ctx()
+    out_h = torch.empty(tuple(go_h.shape)).pin_memory()
+    gv_h, gg_h = torch.empty(tuple(vol_h.shape)).pin_memory(), torch.empty(tuple(grid_h.shape)).pin_memory()
+
+    def ref_lua_step(i):
+        _abi.check(lib.volstn_b200_host_sampler_forward(ctx, 0, 4, d(vol_h), d(grid_h), d(out_h), 0), "fwd")
+        gv_h.zero_(); gg_h.zero_()                                     # lua:101-104
+        _abi.check(lib.volstn_b200_host_sampler_backward(ctx, 0, 4, d(vol_h), d(grid_h), d(gv_h), d(gg_h), d(go_h), 0), "bwd")
+        return float(out_h.view(-1)[0]) + float(gg_h.view(-1)[0])
+
+    t = timed_loop(ref_lua_step)
+    variants["reference_lua_file_flags0"] = {"ms_per_step": t * 1e3, "value": V * n_gpus / t,
+                                             "h2d_bytes_per_step": 2 * (nv + ng) + no + nv, "d2h_bytes_per_step": no + nv + ng,
+                                             "note": "stn3dtorch/BilinearSamplerVolumetric.lua unchanged: host :zero() of both gradInputs, gradVol uploaded (accumulate semantics)"}
+    del out_h, gv_h, gg_h
+    t = timed_loop(sync_step(vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt, reuseForwardInputs=True)))
+    variants["reuse_inputs"] = {"ms_per_step": t * 1e3, "value": V * n_gpus / t, "h2d_bytes_per_step": nv + ng + no, "d2h_bytes_per_step": no + nv + ng,
+                                "note": "opt-in VOLSTN_HOST_KEEP/REUSE_INPUTS: updateGradInput re-uses updateOutput's device copies of volume and grid"}
+    # asynchronous calls, two steps in flight (a module = a set of output buffers per step in flight)
+    for reuse in (False, True):
+        mods = [vnn.BilinearSamplerVolumetric(algo=a.algo << 8, vpt=a.vpt, hostAsync=True, reuseForwardInputs=reuse) for _ in range(2)]
+        tickets = [None, None]
+
+        def collect(k):
+            if tickets[k] is not None:
+                vnn.host_wait(tickets[k])
+                tickets[k] = None
+                return float(mods[k].output.view(-1)[0]) + float(mods[k].gradInput[1].view(-1)[0])
+
+        def async_step(i):
+            k = i & 1
+            collect(k)                                                 # the step issued two steps ago: wait, read its result
+            mods[k].updateOutput([vol_h, grid_h])
+            mods[k].updateGradInput([vol_h, grid_h], go_h)
+            tickets[k] = vnn.host_ticket()
+
+        t = timed_loop(async_step, finish=lambda: (collect(0), collect(1), vnn.host_wait()))
+        variants["async_reuse_inputs" if reuse else "async"] = {
+            "ms_per_step": t * 1e3, "value": V * n_gpus / t,
+            "h2d_bytes_per_step": (nv + ng + no) if reuse else 2 * (nv + ng) + no, "d2h_bytes_per_step": no + nv + ng,
+            "note": "VOLSTN_HOST_ASYNC, two steps in flight: the next step's uploads overlap this step's downloads" + (" + input reuse" if reuse else "")}
+        del mods
+    h2d, d2h = 2 * (nv + ng) + no, no + nv + ng
+    # the host link itself, every rank at the same time (pinned 256 MiB copies): one direction at a time, then both
+    link = None
+    try:
+        nlk = 256 << 20
+        hb, hb2 = torch.empty(nlk, dtype=torch.uint8).pin_memory(), torch.empty(nlk, dtype=torch.uint8).pin_memory()
+        db, db2 = torch.empty(nlk, dtype=torch.uint8, device="cuda"), torch.empty(nlk, dtype=torch.uint8, device="cuda")
+        s2 = torch.cuda.Stream()
+
+        def rate(up, down):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                if up:
+                    db.copy_(hb, non_blocking=True)
+                if down:
+                    with torch.cuda.stream(s2):
+                        hb2.copy_(db2, non_blocking=True)
+            torch.cuda.synchronize()
+            return nlk * 4 / (time.perf_counter() - t0) / 1e9
+
+        rate(True, True)
+        up_gbs, down_gbs, both_gbs = rate(True, False), rate(False, True), rate(True, True)
+        per_rank = None
+        if distributed:
+            tt = torch.tensor([up_gbs, down_gbs, both_gbs], dtype=torch.float64, device="cuda")
+            allr = [torch.empty_like(tt) for _ in range(n_gpus)]
+            dist.all_gather(allr, tt)
+            per_rank = [[round(float(x), 2) for x in r] for r in allr]
+        lb_ms = max(h2d / up_gbs, d2h / down_gbs) / 1e6
+        link = {"h2d_gbs": up_gbs, "d2h_gbs": down_gbs, "each_way_gbs_when_both_run": both_gbs,
+                "per_rank_h2d_d2h_both_gbs": per_rank, "aggregate_h2d_gbs": sum(r[0] for r in per_rank) if per_rank else up_gbs,
+                "aggregate_d2h_gbs": sum(r[1] for r in per_rank) if per_rank else down_gbs,
+                "lower_bound_ms_per_step": lb_ms, "frac_of_link_bound": lb_ms / (sec * 1e3),
+                "numa_node_of_gpu": int(lib.volstn_b200_host_numa_node(local)),
+                "note": "all ranks copy at the same time; the bound is max(upload bytes / h2d rate, download bytes / d2h rate) of this rank's link as measured with every other rank's link busy"}
+        del hb, db, hb2, db2
+    except Exception as e:  # noqa: BLE001
+        link = {"error": repr(e)[:200]}
+    return {"value": V * n_gpus / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": sec * 1e3, "steps": e2e_steps, "link": link, "variants": variants,
+            "path": "volstn_b200_host_sampler_forward/backward as lua/BilinearSamplerVolumetric.lua calls them: pinned host tensors -> sliced H2D / kernels / D2H on 3 streams -> host tensors; synchronous; both calls upload volume and grid (the reference re-reads its inputs)"}
 
 
 def run_aux(a, torch, vnn, synth, _abi, peak):
@@ -792,6 +896,74 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
     return res
 
 
+def _load_train_step():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("volstn_train_step", os.path.join(ROOT, "tools", "train_step.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_train_config(a, torch, dist, rank, n_gpus, distributed):
+    """BASELINE.json config 3: ALIGNet-3D training step at 64^3, GLOBAL batch 64 sharded over the ranks (strong
+    scaling), the one-kernel warp head, one NCCL all-reduce of the CNN gradients (tools/train_step.py)."""
+    ts = _load_train_step()
+    res = ts.run(steps=max(3, min(a.steps, 8)), warmup=3, global_batch=64, size=64, fused=2, rank=rank, world=n_gpus)
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_contention_config(a, torch, dist, rank, n_gpus, distributed):
+    """BASELINE.json config 5: 128^3, C = 4, extreme / out-of-bounds field g4 (5 % exact corners, 1 % of all voxels on ONE
+    point: gradVol contention), 8 samples per GPU; device-resident, CUDA events, max over ranks."""
+    from alignet_b200 import nn as vnn, shard, synth
+    N, C, B = 128, 4, 8
+    rng = np.random.default_rng(50 + rank)
+    vol = torch.from_numpy(synth.volume("v1", 2, N, N, N, C, rng)).cuda().repeat(B // 2, 1, 1, 1, 1).contiguous()
+    grid = torch.from_numpy(synth.grid("g4", 2, N, N, N, rng)).cuda().repeat(B // 2, 1, 1, 1, 1).contiguous()
+    go = torch.randn((B, N, N, N, C), device="cuda")
+    m = vnn.BilinearSamplerVolumetric()
+    for _ in range(3):
+        m.updateOutput([vol, grid]); m.updateGradInput([vol, grid], go)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps, f, b = 5, 0.0, 0.0
+    for _ in range(reps):
+        e[0].record(); m.updateOutput([vol, grid]); e[1].record(); m.updateGradInput([vol, grid], go); e[2].record()
+        torch.cuda.synchronize()
+        f += e[0].elapsed_time(e[1]) / reps; b += e[1].elapsed_time(e[2]) / reps
+    if distributed:
+        f, b = shard.max_over_ranks(f, device="cuda"), shard.max_over_ranks(b, device="cuda")
+    peak, _ = measured_peak()
+    V = B * N ** 3
+    del vol, grid, go
+    torch.cuda.empty_cache()
+    return {"config": "BASELINE.json config 5: 128^3, C=4, field g4 (out of bounds + contention), 8 samples per GPU",
+            "n_gpus": n_gpus, "fwd_ms": f, "bwd_ms": b, "voxels_per_s": V * n_gpus / ((f + b) * 1e-3), "scaling": "weak",
+            "fwd_frac_of_hbm_peak": fwd_bytes(C) * V / (f * 1e-3) / 1e9 / peak, "bwd_frac_of_hbm_peak": bwd_bytes(C) * V / (b * 1e-3) / 1e9 / peak,
+            "step_frac_of_hbm_peak": (fwd_bytes(C) + bwd_bytes(C)) * V / ((f + b) * 1e-3) / 1e9 / peak,
+            "note": "working set 1.5 GiB per GPU (no L2 flush needed); parity of this configuration against the float and double oracles: tests/test_gpu_sampler.py::test_scatter_contention_against_double_oracle"}
+
+
+def run_single_config(a):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fn = run_train_config if a.config == "train" else run_contention_config
+    res = fn(a, torch, dist, rank, world, world > 1)
+    if rank == 0:
+        emit(res)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_sweep(a, torch, vnn, synth, _abi):
     """BASELINE.json config 4: fwd+bwd over sizes x grids, GB/s against the roofline (rank 0, 1 GPU)."""
     peak, _ = measured_peak()
@@ -858,9 +1030,14 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the grid generator / Cumsum / 32^3 pipeline timings")
     ap.add_argument("--no-graph", action="store_true", help="launch the step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-fields", action="store_true", help="skip the extra per-field (g2, g3) device-resident timings")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE.json configs 3 (training step) and 5 (contention)")
+    ap.add_argument("--config", default="sampler", choices=["sampler", "train", "contention"],
+                    help="sampler = the contract line; train / contention = only that configuration, as one JSON line")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.config != "sampler":
+        run_single_config(a)
     else:
         run_ours(a)
 

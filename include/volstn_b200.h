@@ -87,14 +87,30 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_ALGO_MASK 0xF00u
 #define VOLSTN_ALGO_AUTO 0x000u
 #define VOLSTN_ALGO_DIRECT 0x100u /* one red.global per in-bounds corner (vector red for C = 2, 4)   */
-#define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA */
+#define VOLSTN_ALGO_TILE 0x200u   /* shared-memory privatised gradVol tile per CTA, falls back per CTA.  ACCURACY: the tile
+                                     accumulates in fixed point scaled to max|gradOut| of each 256-voxel brick, so a contribution
+                                     is rounded by at most 2^-23 of that maximum (gradVol's contract, 1e-4 * max|ref|, holds; a
+                                     contribution 2^23 times smaller than the brick's largest gradOut is lost).  AUTO takes this
+                                     path only when the output has >= 128 voxels per volume cell (ALIGNet's cage up-sample);
+                                     VOLSTN_ALGO_DIRECT never does */
 #define VOLSTN_ALGO_QUAD 0x400u   /* backward, C = 1: x0/x0+1 contributions as one 16-byte reduction on the aligned quad (AUTO
                                      chooses this per warp when the warp's cells are scattered; DIRECT never does) */
 #define VOLSTN_ALGO_ROW 0x500u    /* the row kernels (a warp per output row; the path of strided / planar tensors) even for packed tensors */
-#define VOLSTN_ALGO_PAIR 0x300u   /* direct kernels with packed fp32x2 arithmetic (measured slower; kept for A/B) */
+/* 0x300 was VOLSTN_ALGO_PAIR (packed fp32x2 arithmetic): measured 12-25 % slower in round 1 and removed from the
+ * library in round 2 (record: profiles/r01_kbench_history.txt); the value now selects the automatic path */
 /* debugging / A-B timing: force the slower but always-valid code paths (results are identical) */
 #define VOLSTN_DEBUG_NO_FAST 0x10000u   /* every warp takes the exact predicated path            */
 #define VOLSTN_DEBUG_NO_BORDER 0x20000u /* warps touching a high face take the exact path (no border tier) */
+/* Cage entry points (volstn_b200_cage_warp_forward / _backward / _step), single-channel volumes: FAST ARITHMETIC.  The
+ * cage up-sample is evaluated in its separable form (per output row the four (y, z) corners are folded into cW + 1
+ * x-nodes once, then every voxel is one linear interpolation between two nodes), the eight-term sums are FMA chains
+ * and gradGrid is factored per axis.  Same mathematics as the default path, different rounding: the up-sampled field
+ * moves by a few ulp, so `out` is within 1e-5 * max|out| of the reference chain instead of bit-identical, and where a
+ * sampling coordinate sits on a cell boundary (the identity cage: every voxel) the source warp may take the
+ * neighbouring cell -- with an interpolation weight within a few ulp of 0 or 1, i.e. the same value, and the OTHER
+ * one-sided derivative for gradCage (the function is only C0 there; the reference's own CUDA path differs from its
+ * CPU path in the same way, its kernels being compiled with FMA contraction).  Off by default. */
+#define VOLSTN_FAST_ARITH 0x40000u
 /* voxels per thread (bits 12..15), 0 = automatic */
 #define VOLSTN_VPT_SHIFT 12
 #define VOLSTN_VPT_MASK 0xF000u
@@ -214,7 +230,10 @@ size_t volstn_b200_gridgen_backward_workspace(int64_t B, int64_t D, int64_t H, i
 
 /* Channel i is prefix-summed along spatial axis i.  Replaces Cumsum:updateOutput's per-channel
  * split/squeeze/cumsum (Cumsum.lua:12-22) with one launch.  Prefixes accumulate in double and are
- * rounded to `dtype` (TH's CPU cumsum uses accreal = double). */
+ * rounded to `dtype` -- TH's CPU cumsum (accreal = double), the parity reference of this repository
+ * (results must match the reference's CPU path).  Known deviation: for torch.CudaTensor the reference
+ * runs cutorch's scan, which accumulates in float; a float prefix can differ from the double-accumulated
+ * one by one ulp.  Both entry-point families (device and host) use the CPU semantics. */
 int volstn_b200_cumsum_forward(int dtype, const void *in, void *out, int64_t B, int N, const int64_t *dims,
                                void *cuda_stream);
 

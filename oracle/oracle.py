@@ -166,24 +166,32 @@ def sampler_indices(vol_shape, grid: np.ndarray):
     return idx, mask
 
 
-def sampler_forward_backward_threaded(vol, grid, grad_out, G=4, impl="ref", threads=1):
+def sampler_forward_backward_threaded(vol, grid, grad_out, G=4, impl="ref", threads=1, bufs=None):
     """Batch-sliced fwd+bwd over `threads` host threads (ctypes releases the GIL).  Valid because
     samples are independent (batch is the outermost loop, ...c:482,641).  Used only as the timed
-    CPU baseline."""
+    CPU baseline.  One call = what the Lua module does per step: updateOutput into self.output (resized once, i.e.
+    pre-allocated: pass `bufs`), then updateGradInput = zero-fill of BOTH gradInputs
+    (BilinearSamplerVolumetric.lua:101-104) + the C function."""
     B = vol.shape[0]
     threads = max(1, min(threads, B))
-    out = np.empty(grid.shape[:4] + (vol.shape[4],), vol.dtype)
-    gv = np.zeros_like(vol)
-    gg = np.zeros_like(grid)
+    if bufs is None:
+        bufs = {}
+    if "out" not in bufs:
+        bufs["out"] = np.empty(grid.shape[:4] + (vol.shape[4],), vol.dtype)
+        bufs["gv"] = np.empty_like(vol)
+        bufs["gg"] = np.empty_like(grid)
+    out, gv, gg = bufs["out"], bufs["gv"], bufs["gg"]
     bounds = np.linspace(0, B, threads + 1).astype(int)
+    lib_call = _backward_into
 
     def work(i):
         lo, hi = bounds[i], bounds[i + 1]
         if hi <= lo:
             return
         sampler_forward(vol[lo:hi], grid[lo:hi], G, impl, out=out[lo:hi])
-        _, g = sampler_backward(vol[lo:hi], grid[lo:hi], grad_out[lo:hi], G, impl, grad_vol=gv[lo:hi])
-        gg[lo:hi] = g
+        gv[lo:hi] = 0          # lua:103 gradInput[i]:resizeAs(input[i]):zero()
+        gg[lo:hi] = 0
+        lib_call(vol[lo:hi], grid[lo:hi], grad_out[lo:hi], gv[lo:hi], gg[lo:hi], G, impl)
 
     if threads == 1:
         work(0)
@@ -194,6 +202,19 @@ def sampler_forward_backward_threaded(vol, grid, grad_out, G=4, impl="ref", thre
         for t in ts:
             t.join()
     return out, gv, gg
+
+
+def _backward_into(vol, grid, grad_out, grad_vol, grad_grid, G, impl):
+    """the backward C function on caller-owned gradient tensors (no allocation inside the timed baseline)"""
+    ts = [_desc(vol), _desc(grid), _desc(grad_vol), _desc(grad_grid), _desc(grad_out)]
+    if impl == "port":
+        fn = getattr(port_lib(), "oracle_sampler_backward_" + _suffix(vol.dtype))
+        rc = fn(ctypes.c_int(G), *[ctypes.byref(t) for t in ts], ctypes.c_int(0))
+        assert rc == 0
+    else:
+        arr = (_Tensor5 * 5)(*ts)
+        rc = ref_lib(vol.dtype).ref_call(1 if G == 4 else 3, 5, arr)
+        assert rc == 1
 
 
 # --------------------------------------------------------------------------------------------
@@ -280,8 +301,23 @@ def smooth_l1_backward(inp: np.ndarray, target: np.ndarray, size_average: bool =
     return np.where(x < -1, -norm, np.where(x > 1, norm, norm * x)).astype(inp.dtype)
 
 
+def iou_reference(pred: np.ndarray, target: np.ndarray) -> float:
+    """computeIOU exactly as util.lua:110-120 writes it, including its grouping: the thresholded tensors (B-major,
+    first channel) are viewed as ``(-1, B)`` and summed over dim 1, so "column c" collects the elements whose FLAT index
+    is congruent to c modulo B -- NOT sample c.  Returns mean_c(intersection_c / union_c)."""
+    B = pred.shape[0]
+    t = (target.reshape(B, -1) > 0.5).astype(np.float64).reshape(-1, B)     # :view(-1, B) of the contiguous tensor
+    e = (pred.reshape(B, -1) > 0.5).astype(np.float64).reshape(-1, B)
+    s = t + e
+    inter, union = (s == 2).sum(0).astype(np.float64), (s > 0).sum(0).astype(np.float64)
+    return float((inter / union).sum() / B)
+
+
 def iou_counts(pred: np.ndarray, target: np.ndarray):
-    """util.lua:113-117: t = target > 0.5, et = pred > 0.5; per sample (#(t and et), #(t or et))."""
+    """PER-SAMPLE (#(t and et), #(t or et)) with t = target > 0.5, et = pred > 0.5 (the thresholds of util.lua:113-114).
+    This is what the fused step kernels count.  It is a DELIBERATE deviation from computeIOU's grouping (see
+    iou_reference): per-sample intersection over union is what the metric's name says; the reference's modulo-B
+    grouping is reproduced by alignet_b200.nn.computeIOU on the kept output, not by the kernel."""
     B = pred.shape[0]
     t, e = target.reshape(B, -1) > 0.5, pred.reshape(B, -1) > 0.5
     return np.stack([(t & e).sum(1), (t | e).sum(1)], 1).astype(np.uint64)

@@ -73,11 +73,11 @@ def test_float_parity_random(G, C, gk):
     ref_out = oracle.sampler_forward(vol, grid, G)
     ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go, G)
     for vpt in (0, 1, 2, 4):
-        for algo in (_abi.ALGO_AUTO, _abi.ALGO_TILE, _abi.ALGO_PAIR):
+        for algo in (_abi.ALGO_AUTO, _abi.ALGO_TILE):
             out = cuda_forward(vol, grid, G, vpt=vpt, algo=algo)
             assert bits_equal(out, ref_out), (vpt, algo, describe_mismatch(out, ref_out))
     for vpt in (0, 1, 2):
-        for algo in (_abi.ALGO_AUTO, _abi.ALGO_DIRECT, _abi.ALGO_TILE, _abi.ALGO_PAIR, _abi.ALGO_QUAD):
+        for algo in (_abi.ALGO_AUTO, _abi.ALGO_DIRECT, _abi.ALGO_TILE, _abi.ALGO_QUAD):
             gv, gg = cuda_backward(vol, grid, go, G, vpt=vpt, algo=algo)
             assert bits_equal(gg, ref_gg), (vpt, algo, describe_mismatch(gg, ref_gg))
             assert_gradvol_close(gv, ref_gv, (vpt, algo))
@@ -292,6 +292,115 @@ def test_full_size_properties(N, B, C):
         rgv, rgg = oracle.sampler_backward(vol_np[b:b + 1], gnp[b:b + 1], go[b:b + 1].cpu().numpy())
         assert bits_equal(gg_a[b:b + 1].cpu().numpy(), rgg)
         assert_gradvol_close(gv_a[b:b + 1].cpu().numpy(), rgv)
+
+
+@pytest.mark.parametrize("gk", ["g1", "g2"])
+def test_headline_shape_first_middle_last_sample(gk):
+    """64^3 x batch 64, C = 1 -- the shape bench.py's headline is quoted on: the packed kernels then run with
+    gridDim.y < B, every CTA walking several samples (batch_rows, sampler.cu).  First, middle and last sample of the
+    batch against the reference's C code: out and gradGrid bit for bit, gradVol within 1e-4 of max|ref|."""
+    N, B = 64, 64
+    rng = np.random.default_rng(64 + len(gk))
+    vol_np = synth.volume("v2", B, N, N, N, 1, rng)
+    grid_np = synth.grid(gk, B, N, N, N, rng)
+    go_np = synth.grad_output(B, N, N, N, 1, rng)
+    vol, grid, go = dev(vol_np), dev(grid_np), dev(go_np)
+    m = vnn.BilinearSamplerVolumetric()
+    out = m.updateOutput([vol, grid])
+    gv, gg = m.updateGradInput([vol, grid], go)
+    for b in (0, 1, B // 2 - 1, B // 2, B - 2, B - 1):
+        sl = slice(b, b + 1)
+        assert bits_equal(out[sl].cpu().numpy(), oracle.sampler_forward(vol_np[sl], grid_np[sl])), b
+        rgv, rgg = oracle.sampler_backward(vol_np[sl], grid_np[sl], go_np[sl])
+        assert bits_equal(gg[sl].cpu().numpy(), rgg), b
+        assert_gradvol_close(gv[sl].cpu().numpy(), rgv)
+
+
+def test_largest_admissible_sample_32bit_offsets():
+    """The packed kernels form in-sample offsets in WRAPPING 32-bit arithmetic (sampler.cuh: finish_fast, base32,
+    CornerRows); admission is `elements per sample < 2^31` (packed_ok).  One sample of 1024 x 1024 x 2047 voxels =
+    2 146 435 072 elements sits 1 048 576 below that limit: the corners of its LAST voxels have offsets just under
+    2^31 on every tier (fast: interior; border: exactly on the high faces; exact: straddling them).  Checked against
+    the reference's C code (it indexes with `int`, ...c:519-529, valid up to exactly this size)."""
+    D, H, W = 1024, 1024, 2047
+    assert D * H * W < 2 ** 31 <= D * H * (W + 1)
+    rng = np.random.default_rng(2047)
+    vol_np = np.zeros((1, D, H, W, 1), np.float32)        # calloc: only the touched slabs become resident
+    for z in (0, 1, D - 2, D - 1):
+        vol_np[0, z] = rng.standard_normal((H, W, 1)).astype(np.float32)
+    vol = torch.zeros((1, D, H, W, 1), device="cuda")
+    for z in (0, 1, D - 2, D - 1):
+        vol[0, z] = torch.from_numpy(vol_np[0, z]).cuda()
+    oD, oH, oW = 4, 8, 64
+    grid_np = np.ones((1, oD, oH, oW, 4), np.float32)
+
+    def norm(c, n):      # a coordinate whose un-normalised value is ~c (the kernel recomputes it like the reference)
+        return (2.0 * c / (n - 1) - 1.0).astype(np.float32)
+
+    # plane 0: strictly inside the last cell block (fast tier: every corner of every lane in bounds)
+    grid_np[0, 0, ..., 0] = norm(rng.uniform(D - 2, D - 1.001, (oH, oW)), D)
+    grid_np[0, 0, ..., 1] = norm(rng.uniform(H - 3, H - 1.001, (oH, oW)), H)
+    grid_np[0, 0, ..., 2] = norm(rng.uniform(W - 40, W - 1.001, (oH, oW)), W)
+    # plane 1: exactly on the high faces (+1 -> size-1: border tier, high corners out of bounds with weight 0)
+    grid_np[0, 1, ..., 0] = 1.0
+    grid_np[0, 1, ..., 1] = np.where(rng.random((oH, oW)) < 0.5, 1.0, norm(rng.uniform(H - 3, H - 1.001, (oH, oW)), H))
+    grid_np[0, 1, ..., 2] = np.where(rng.random((oH, oW)) < 0.5, 1.0, norm(rng.uniform(W - 40, W - 1.001, (oH, oW)), W))
+    # plane 2: straddling the far corner (exact tier: some corners out of bounds with non-zero weight)
+    grid_np[0, 2, ..., 0] = norm(rng.uniform(D - 2, D + 0.5, (oH, oW)), D)
+    grid_np[0, 2, ..., 1] = norm(rng.uniform(H - 2, H + 0.5, (oH, oW)), H)
+    grid_np[0, 2, ..., 2] = norm(rng.uniform(W - 2, W + 0.5, (oH, oW)), W)
+    # plane 3: the near corner and anywhere
+    grid_np[0, 3, ..., :3] = rng.uniform(-1.001, 1.001, (oH, oW, 3)).astype(np.float32)
+    grid_np[0, 3, :2, :, :3] = -1.0 + rng.uniform(0, 2e-3, (2, oW, 3)).astype(np.float32)
+    go_np = synth.grad_output(1, oD, oH, oW, 1, rng)
+    ref = oracle.sampler_forward(vol_np, grid_np)
+    gv_ref = np.zeros((1, D, H, W, 1), np.float32)
+    _, gg_ref = oracle.sampler_backward(vol_np, grid_np, go_np, grad_vol=gv_ref)
+    idx, mask = oracle.sampler_indices(vol_np.shape, grid_np)
+    grid, go = dev(grid_np), dev(go_np)
+    for vpt in (0, 1):                                   # two and one voxel per thread: different CTA / plane mapping
+        m = vnn.BilinearSamplerVolumetric(vpt=vpt)
+        out = m.updateOutput([vol, grid])
+        assert bits_equal(out.cpu().numpy(), ref), describe_mismatch(out.cpu().numpy(), ref)
+        gv, gg = m.updateGradInput([vol, grid], go)
+        assert bits_equal(gg.cpu().numpy(), gg_ref)
+        # gradVol: compare at every cell any corner touches, and nowhere else may anything be non-zero
+        cells = set()
+        for (z0, y0, x0), mk in zip(idx.tolist(), mask.tolist()):
+            for k in range(8):
+                if mk >> k & 1:
+                    cells.add(((z0 + (k >> 2 & 1)) * H + y0 + (k >> 1 & 1)) * W + x0 + (k & 1))
+        cells = np.array(sorted(cells), np.int64)
+        assert cells.max() == D * H * W - 1                   # the very last element of the sample is written
+        got = gv.view(-1)[torch.from_numpy(cells).cuda()].cpu().numpy()
+        want = gv_ref.reshape(-1)[cells]
+        assert np.max(np.abs(got - want)) <= 1e-4 * np.max(np.abs(want))
+        assert int(torch.count_nonzero(gv)) == int(np.count_nonzero(want))
+    di, dm = vnn.BilinearSamplerVolumetric().indices(vol, grid)
+    assert np.array_equal(di.cpu().numpy(), idx) and np.array_equal(dm.cpu().numpy(), mask)
+
+
+def test_small_volume_backward_wide_dynamic_range():
+    """VOLSTN_ALGO_AUTO sends a backward whose volume is much smaller than its output (ALIGNet's cage up-sample) to the
+    shared-memory kernel, which accumulates in FIXED POINT scaled to max|gradOut| of each 256-voxel brick (header:
+    contributions below 2^-23 of that maximum are rounded away).  The contract stays the one stated for gradVol --
+    1e-4 of max|ref| -- also when gradOut spans nine decades; VOLSTN_ALGO_DIRECT keeps the small contributions."""
+    rng = np.random.default_rng(99)
+    B, N, c = 2, 32, 4
+    vol = synth.volume("v1", B, c, c, c, 4, rng)
+    grid = synth.grid("g1", B, N, N, N, rng)
+    go = (1e-3 * synth.grad_output(B, N, N, N, 4, rng)).astype(np.float32)
+    go[0, 3, 5, 7, :] = 1e6                                   # one outlier in one brick
+    go[1, N // 2:, :, :, :] *= 1e5
+    ref64, _ = oracle.sampler_backward(vol.astype(np.float64), grid.astype(np.float64), go.astype(np.float64))
+    for algo in (_abi.ALGO_AUTO, _abi.ALGO_DIRECT):
+        gv, gg = cuda_backward(vol, grid, go, algo=algo)
+        assert max_rel(gv.astype(np.float64), ref64) <= 1e-4, (algo, max_rel(gv.astype(np.float64), ref64))
+        _, rgg = oracle.sampler_backward(vol, grid, go)
+        assert bits_equal(gg, rgg)
+    # the direct kernel resolves sample 1's small half to fp32 accuracy; the fixed-point one only to its stated step
+    gv_d, _ = cuda_backward(vol, grid, go, algo=_abi.ALGO_DIRECT)
+    assert max_rel(gv_d[1].astype(np.float64), ref64[1]) <= 1e-5
 
 
 def test_empty_and_degenerate_shapes():

@@ -178,3 +178,28 @@ def test_cumsum_restatement_agrees_with_aten_cpu():
         t = torch.from_numpy(g[:, i])
         got = torch.flip(torch.cumsum(torch.flip(t, [1 + i]), dim=1 + i), [1 + i]).numpy()   # Cumsum.lua:44-47
         assert np.array_equal(got.view(np.uint32), refb[:, i].view(np.uint32)), i
+
+
+def test_compute_iou_reference_grouping_is_modulo_batch():
+    """util.lua:115-116 views the B-major tensor as (-1, B) and sums over dim 1: column c = flat indices congruent to c
+    modulo B, not sample c.  The restatement reproduces that; the per-sample counts the fused kernels produce are a
+    documented deviation.  The torch mirror (alignet_b200.nn.computeIOU) equals the restatement."""
+    import torch
+    from alignet_b200 import nn as vnn
+    rng = np.random.default_rng(12)
+    B, n = 3, 8
+    pred = rng.random((B, 1, 2, 2, 2)).astype(np.float32)
+    tgt = (rng.random((B, 1, 2, 2, 2)) > 0.4).astype(np.float32)
+    ref = oracle.iou_reference(pred, tgt)
+    # by hand, from the definition
+    t, e = (tgt.reshape(-1) > 0.5), (pred.reshape(-1) > 0.5)
+    by_hand = 0.0
+    for c in range(B):
+        idx = np.arange(c, B * n, B)
+        by_hand += float((t[idx] & e[idx]).sum()) / float((t[idx] | e[idx]).sum())
+    assert abs(ref - by_hand / B) <= 1e-15
+    counts = oracle.iou_counts(pred, tgt).astype(np.float64)
+    per_sample = float(np.mean(counts[:, 0] / counts[:, 1]))
+    assert abs(per_sample - ref) > 1e-6                      # the two groupings are different numbers
+    got = float(vnn.computeIOU(torch.from_numpy(pred), torch.from_numpy(tgt)))
+    assert abs(got - ref) <= 1e-15

@@ -111,6 +111,15 @@ def main():
         b_ff = timed(lambda: fus_full.updateGradInput([vol, cage], go))
         report("cage chain bwd (full warp bwd + up-sample bwd)", b_wf + b_up, 76 * V, f"({b_wf:.1f} + {b_up:.1f})")
         report("cage FUSED bwd (gradSource + gradCage)", b_ff, 12 * V, f"x{(b_wf + b_up) / b_ff:.2f}")
+        # VOLSTN_FAST_ARITH: separable cage up-sample, FMA sums, factored gradGrid (tolerance mode)
+        fast, fast_full = vnn.CageWarpVolumetric(onlyGrid=True, fastArith=True), vnn.CageWarpVolumetric(fastArith=True)
+        report("cage FUSED fwd, fast arithmetic", timed(lambda: fast.updateOutput([vol, cage])), 8 * V, f"x{f_fus / timed(lambda: fast.updateOutput([vol, cage])):.2f} over exact")
+        report("cage FUSED bwd (gradCage only), fast arithmetic", timed(lambda: fast.updateGradInput([vol, cage], go)), 8 * V)
+        report("cage FUSED bwd (gradSource + gradCage), fast arithmetic", timed(lambda: fast_full.updateGradInput([vol, cage], go)), 12 * V)
+        tgt = rep(synth.volume("v2", nb, N, N, N, 1, rng))
+        for fa in (False, True):
+            stp = vnn.CageWarpSmoothL1Volumetric(fastArith=fa)
+            report(f"cage STEP (fwd + SmoothL1 + IoU + bwd to the cage){', fast arithmetic' if fa else ''}", timed(lambda: stp.forwardBackward([vol, cage], tgt)), 8 * V)
         del field, field_i, gfield
 
     if "cf1" in what:

@@ -12,13 +12,14 @@ from alignet_b200 import nn as vnn
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=64); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--csz", type=int, default=8)
 ap.add_argument("--what", default="packed,row,affine,cage,step,cf")
+ap.add_argument("--grid", default="g1", help="warp field family of the plain sampler launches (g1 identity, g2 ALIGNet-like, g3 uniform random)")
 a = ap.parse_args()
 N, B, csz = a.size, a.batch, a.csz
 rng = np.random.default_rng(7)
 nb = min(B, 8)
 rep = lambda x: torch.from_numpy(x).cuda().repeat(B // nb, *([1] * (x.ndim - 1))).contiguous()
 vol = rep(synth.volume("v2", nb, N, N, N, 1, rng)); go = torch.randn((B, N, N, N, 1), device="cuda")
-grid = rep(synth.grid("g1", nb, N, N, N, rng))
+grid = rep(synth.grid(a.grid, nb, N, N, N, rng))
 T = torch.eye(4, device="cuda").repeat(B, 1, 1) + 0.02 * torch.randn(B, 4, 4, device="cuda")
 cage = torch.from_numpy(synth.alignet_cage(nb, csz, rng).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
 what = a.what.split(",")

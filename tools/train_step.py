@@ -51,6 +51,108 @@ class WarpNet(tnn.Module):
         return vag.cumsum(d.contiguous(), self.cumsum) + self.beta      # nn.Cumsum -> + beta (lua:102-112)
 
 
+def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
+    """The training step on an ALREADY initialised process group (bench.py --config train and the bench line's `train`
+    section call this; main() below is the stand-alone launcher).  Returns the result dict on every rank."""
+    N, csz = size, 4
+    lo, hi = shard.batch_slice(global_batch, world, rank)
+    B = hi - lo
+    torch.manual_seed(0)                                                # identical weights on every rank
+    net = WarpNet(csz).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    rng = np.random.default_rng(100 + rank)
+    src = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()          # B x D x H x W x 1
+    tgt = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()
+    pair = torch.stack([src[..., 0], tgt[..., 0]], dim=1).contiguous()              # B x 2 x D x H x W
+    field_i = None
+    if fused == 0:
+        gen = vnn.VolumetricGridGenerator(N, N, N)
+        field_i = gen.updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))     # constant, like fieldI (dataset_2d.lua:128)
+    up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
+    fwarp, fstep = vnn.CageWarpVolumetric(), vnn.CageWarpSmoothL1Volumetric()
+    params = [p for p in net.parameters()]
+    crit = tnn.SmoothL1Loss()
+    ones = torch.ones((B, csz, csz, csz, 1), device="cuda")
+    flat = torch.empty(sum(p.numel() for p in params), device="cuda")
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("cnn_fwd", "warp", "cnn_bwd", "allreduce", "adam")}
+
+    def mark(timed, key, i):
+        if timed:
+            ev[key][i].record()
+
+    def step(timed=False):
+        opt.zero_grad(set_to_none=True)
+        mark(timed, "cnn_fwd", 0)
+        cage = net(pair)                                                            # B x 3 x csz^3
+        mark(timed, "cnn_fwd", 1)
+        mark(timed, "warp", 0)
+        if fused == 2:                                                              # warp + criterion + both backwards: one kernel
+            loss = vag.cage_warp_smooth_l1(src, cage.contiguous(), tgt, fstep)
+        else:
+            if fused == 1:
+                est = vag.cage_warp_volumetric(src, cage.contiguous(), fwarp)       # cage up-sample + source warp: one kernel
+            else:
+                cage_vol = torch.cat([cage.permute(0, 2, 3, 4, 1), ones], dim=-1).contiguous()   # channels-last, 4th coord
+                field = vag.bilinear_sampler_volumetric(cage_vol, field_i, up)      # cage up-sample -> B x N^3 x 4
+                est = vag.bilinear_sampler_volumetric(src, field, warp)             # source warp
+            loss = crit(est, tgt)
+        mark(timed, "warp", 1)
+        mark(timed, "cnn_bwd", 0)
+        loss.backward()
+        mark(timed, "cnn_bwd", 1)
+        mark(timed, "allreduce", 0)
+        if world > 1:                                                               # the one collective of the step
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+            dist.all_reduce(flat)
+            flat.div_(world)
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        mark(timed, "allreduce", 1)
+        mark(timed, "adam", 0)
+        opt.step()
+        mark(timed, "adam", 1)
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _abi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (_abi.launch_count() - n0) // steps
+    if world > 1:
+        dist.barrier()
+        ms = shard.max_over_ranks(ms, device="cuda")
+    # where the step goes: one more step with events around its stages (device time of each stage on this rank; for
+    # fused = 2 "warp" is forward + criterion + the warp's backward in one kernel and "cnn_bwd" the CNN's backward alone)
+    parts = {k: 0.0 for k in ev}
+    reps = 3
+    for _ in range(reps):
+        step(True); torch.cuda.synchronize()
+        for k in ev:
+            parts[k] += ev[k][0].elapsed_time(ev[k][1]) / reps
+    if world > 1:
+        parts = {k: shard.max_over_ranks(v, device="cuda") for k, v in parts.items()}
+        dist.barrier()
+    nparam = sum(p.numel() for p in params)
+    limiter = max(parts, key=parts.get)
+    return {"config": "ALIGNet-3D training step (BASELINE.json config 3)", "size": N, "global_batch": global_batch,
+            "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "samples_per_s": global_batch / (ms * 1e-3),
+            "voxels_per_s": global_batch * N ** 3 / (ms * 1e-3), "loss": float(loss.detach()),
+            "stage_ms": parts, "largest_stage": limiter, "fused": fused, "volstn_kernels_per_step": int(launches),
+            "allreduce_floats": nparam if world > 1 else 0, "allreduce_us": parts["allreduce"] * 1e3, "scaling": "strong",
+            "note": "CNN = plain PyTorch / cuDNN fp32 Conv3d (3-D lift of models/alignet_2d.lua:33-57; library code); Cumsum and the "
+                    "warp head = this repo's kernels; one NCCL all-reduce of the flattened CNN gradients per step (flatten + "
+                    "all-reduce + un-flatten timed together as `allreduce`)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
@@ -62,77 +164,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, csz = a.size, 4
-    lo, hi = shard.batch_slice(a.global_batch, world, rank)
-    B = hi - lo
-    torch.manual_seed(0)                                                # identical weights on every rank
-    net = WarpNet(csz).cuda()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    rng = np.random.default_rng(100 + rank)
-    src = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()          # B x D x H x W x 1
-    tgt = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()
-    pair = torch.stack([src[..., 0], tgt[..., 0]], dim=1).contiguous()              # B x 2 x D x H x W
-    gen = vnn.VolumetricGridGenerator(N, N, N)
-    field_i = gen.updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))         # constant, like fieldI (dataset_2d.lua:128)
-    up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
-    fwarp, fstep = vnn.CageWarpVolumetric(), vnn.CageWarpSmoothL1Volumetric()
-    params = [p for p in net.parameters()]
-    crit = tnn.SmoothL1Loss()
-    ones = torch.ones((B, csz, csz, csz, 1), device="cuda")
-
-    def step(timers=None):
-        opt.zero_grad(set_to_none=True)
-        cage = net(pair)                                                            # B x 3 x csz^3
-        cage_vol = torch.cat([cage.permute(0, 2, 3, 4, 1), ones], dim=-1).contiguous()   # channels-last, 4th coord
-        if timers: timers[0].record()
-        if a.fused == 2:                                                            # warp + criterion + both backwards: one kernel
-            loss = vag.cage_warp_smooth_l1(src, cage.contiguous(), tgt, fstep)
-            if timers: timers[1].record()
-        else:
-            if a.fused == 1:
-                est = vag.cage_warp_volumetric(src, cage.contiguous(), fwarp)       # cage up-sample + source warp: one kernel
-            else:
-                field = vag.bilinear_sampler_volumetric(cage_vol, field_i, up)      # cage up-sample -> B x N^3 x 4
-                est = vag.bilinear_sampler_volumetric(src, field, warp)             # source warp
-            if timers: timers[1].record()
-            loss = crit(est, tgt)
-        loss.backward()
-        if world > 1:                                                               # the one collective of the step
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat); flat /= world
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
-        opt.step()
-        return loss
-
-    for _ in range(a.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1: dist.barrier()
-    n0 = _abi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        loss = step()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
-    launches = (_abi.launch_count() - n0) // a.steps
-    if world > 1:
-        ms = shard.max_over_ranks(ms, device="cuda")
-    # warp-path forward share (two samplers) inside one more step
-    t = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    step(t); torch.cuda.synchronize()
-    warp_fwd_ms = t[0].elapsed_time(t[1])
-    nparam = sum(p.numel() for p in params)
+    res = run(a.steps, a.warmup, a.global_batch, a.size, a.fused, rank, world)
     if rank == 0:
-        print(json.dumps({"config": "ALIGNet-3D training step (BASELINE.json config 3)", "size": N, "global_batch": a.global_batch,
-                          "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "samples_per_s": a.global_batch / (ms * 1e-3),
-                          "voxels_per_s": a.global_batch * N ** 3 / (ms * 1e-3), "loss": float(loss.detach()),
-                          "warp_forward_ms": warp_fwd_ms, "fused": a.fused, "volstn_kernels_per_step": int(launches),
-                          "allreduce_floats": nparam if world > 1 else 0, "scaling": "strong",
-                          "note": "CNN = plain PyTorch (3-D lift of models/alignet_2d.lua); Cumsum, grid generator and both samplers = this repo's kernels; one NCCL all-reduce of the CNN gradients per step"}),
-              file=out_fd, flush=True)
+        print(json.dumps(res), file=out_fd, flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
