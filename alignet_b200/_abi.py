@@ -22,7 +22,7 @@ HOST_KEEP_INPUTS = 0x8
 HOST_REUSE_INPUTS = 0x10
 HOST_ASYNC = 0x20
 FAST_ARITH = 0x40000
-ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_QUAD, ALGO_ROW = 0x000, 0x100, 0x200, 0x400, 0x500
+ALGO_AUTO, ALGO_DIRECT, ALGO_TILE, ALGO_QUAD, ALGO_ROW, ALGO_TMA = 0x000, 0x100, 0x200, 0x400, 0x500, 0x600
 VPT_SHIFT = 12
 
 

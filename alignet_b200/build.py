@@ -22,7 +22,7 @@ BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libvolstn_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "rowwarp.cu", "fused_api.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
+SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "sampler_tma.cu", "rowwarp.cu", "fused_api.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
 HEADERS = ["volstn_common.cuh", "sampler.cuh", "rowwarp.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
 
 NVCC_FLAGS = [

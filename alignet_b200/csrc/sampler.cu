@@ -696,6 +696,7 @@ int sampler_forward_impl(int dtype, int G, const volstn_tensor5 *vol, const vols
     if (flags & VOLSTN_DEBUG_NO_BORDER) a.border_ok = 0;
     const bool force_row = (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW;
     if (!force_row && packed_ok(G, vol, {grid, out})) {
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TMA && tma_supported(a, nullptr)) return launch_fwd_tma(a, G, st);
       const int vpt = pick_vpt(flags, a.C, a.n);
       return G == 4 ? dispatch_fwd_packed<4>(a, vpt, st) : dispatch_fwd_packed<3>(a, vpt, st);
     }
@@ -764,6 +765,8 @@ int sampler_backward_impl(int dtype, int G, const volstn_tensor5 *vol, const vol
           reinterpret_cast<uintptr_t>(a.gvol) % 16 == 0)
         a.quad = 2;
       a.tile_agg = a.n >= 128LL * a.iD * a.iH * a.iW;
+      if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TMA && !ov && tma_supported(a, og ? nullptr : a.gvol))
+        return launch_bwd_tma(a, G, og, st);
       if ((flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_TILE && !og && tile_supported(a))
         return launch_bwd_tile(a, G, ov, st);
       // Automatic choice: a volume much smaller than the output (ALIGNet's cage up-sample: 16.8 M voxels scatter

@@ -492,6 +492,10 @@ __device__ __forceinline__ void voxel_backward_packed(const SamplerArgs<real> &a
 }
 
 // shared-memory privatised backward (sampler_tile.cu): packed float tensors, C in {1, 2, 4}, 16-byte rows
+// TMA-staged kernels (sampler_tma.cu): packed single-channel float tensors, 16-byte volume rows
+bool tma_supported(const SamplerArgs<float> &a, const float *gvol);
+int launch_fwd_tma(const SamplerArgs<float> &a, int G, cudaStream_t st);
+int launch_bwd_tma(const SamplerArgs<float> &a, int G, bool only_grid, cudaStream_t st);
 bool tile_supported(const SamplerArgs<float> &a);
 int launch_bwd_tile(const SamplerArgs<float> &a, int G, bool only_vol, cudaStream_t st);
 

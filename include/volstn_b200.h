@@ -95,6 +95,10 @@ typedef struct volstn_tensor5 {
                                      VOLSTN_ALGO_DIRECT never does */
 #define VOLSTN_ALGO_QUAD 0x400u   /* backward, C = 1: x0/x0+1 contributions as one 16-byte reduction on the aligned quad (AUTO
                                      chooses this per warp when the warp's cells are scattered; DIRECT never does) */
+#define VOLSTN_ALGO_TMA 0x600u    /* single-channel packed float tensors: a CTA per 8^3 output brick, the bounding box of its volume cells
+                                     staged in shared memory by ONE TMA box load (hardware zero fill = the reference's padding rule),
+                                     gradVol privatised in fixed point and flushed by ONE TMA box reduction; out / gradGrid keep the
+                                     reference's bits, gradVol as VOLSTN_ALGO_TILE.  For sheared warp fields; opt-in */
 #define VOLSTN_ALGO_ROW 0x500u    /* the row kernels (a warp per output row; the path of strided / planar tensors) even for packed tensors */
 /* 0x300 was VOLSTN_ALGO_PAIR (packed fp32x2 arithmetic): measured 12-25 % slower in round 1 and removed from the
  * library in round 2 (record: profiles/r01_kbench_history.txt); the value now selects the automatic path */

@@ -490,3 +490,55 @@ def test_small_volume_under_large_output_uses_privatised_backward(C, gk):
     ones = np.ones_like(go)
     gv, _ = cuda_backward(vol, grid, ones)
     assert_gradvol_close(gv, oracle.sampler_backward(vol, grid, ones)[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# VOLSTN_ALGO_TMA: the volume box of an 8^3 output brick staged by one TMA load (zero fill = the reference's padding),
+# gradVol privatised and flushed by one TMA reduction.  Same contract as the direct kernels.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G", [4, 3])
+@pytest.mark.parametrize("gk", ["g1", "g2", "g3", "g4", "g5"])
+@pytest.mark.parametrize("ishape,oshape", [((9, 11, 12), (7, 10, 37)), ((16, 16, 16), (16, 16, 16)), ((5, 6, 8), (20, 9, 8)), ((32, 32, 32), (24, 24, 24))])
+def test_tma_staged_kernels_match_the_reference(G, gk, ishape, oshape):
+    rng = np.random.default_rng(600 + G + ord(gk[1]) + ishape[0] + oshape[2])
+    B = 3
+    vol = synth.volume("v1", B, *ishape, 1, rng)
+    grid = synth.grid(gk, B, *oshape, rng, G=G, csz=4)
+    if gk == "g4":
+        grid[0, 0, 0, :4, :3] = [np.nan, np.inf, -np.inf]           # not stageable: that brick takes the direct code
+        grid[1, 1, 1, 1, :3] = 1e30
+    go = synth.grad_output(B, *oshape, 1, rng)
+    ref_out = oracle.sampler_forward(vol, grid, G)
+    ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go, G)
+    out = cuda_forward(vol, grid, G, algo=_abi.ALGO_TMA)
+    assert bits_equal(out, ref_out), describe_mismatch(out, ref_out)
+    gv, gg = cuda_backward(vol, grid, go, G, algo=_abi.ALGO_TMA)
+    assert bits_equal(gg, ref_gg), describe_mismatch(gg, ref_gg)
+    assert_gradvol_close(gv, ref_gv, (G, gk))
+    gv2, gg2 = cuda_backward(vol, grid, go, G, algo=_abi.ALGO_TMA, onlyGrid=True)
+    assert bits_equal(gg2, ref_gg) and not gv2.any()
+
+
+def test_tma_staged_kernels_accumulate_and_use_tma():
+    """gradVol is accumulated into (no zero-fill flag) by the TMA reduction like by the direct reductions; the library
+    carries the TMA instructions (UTMALDG / UTMAREDG in its SASS is checked on the build side, profiles/r02_sass.md)."""
+    rng = np.random.default_rng(611)
+    B, N = 2, 24
+    vol = synth.volume("v1", B, N, N, N, 1, rng)
+    grid = synth.grid("g2", B, N, N, N, rng, csz=4)
+    go = synth.grad_output(B, N, N, N, 1, rng)
+    init = rng.standard_normal(vol.shape).astype(np.float32)
+    rgv, rgg = oracle.sampler_backward(vol, grid, go, grad_vol=init.copy())
+    tv, tg, tgo = dev(vol), dev(grid), dev(go)
+    gv, gg = dev(init), torch.empty_like(tg)
+    d = vnn._desc
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n0 = _abi.launch_count()
+    _abi.check(_abi.lib().volstn_b200_sampler_backward(0, 4, d(tv), d(tg), d(gv), d(gg), d(tgo), _abi.ALGO_TMA, st), "bwd")
+    assert _abi.launch_count() - n0 == 1
+    assert bits_equal(gg.cpu().numpy(), rgg)
+    assert_gradvol_close(gv.cpu().numpy(), rgv)
+    # unsupported shapes (W not a multiple of 4, C > 1) quietly take the automatic path
+    vol2 = synth.volume("v1", B, 7, 9, 13, 2, rng)
+    grid2 = synth.grid("g3", B, 6, 7, 9, rng)
+    assert bits_equal(cuda_forward(vol2, grid2, algo=_abi.ALGO_TMA), oracle.sampler_forward(vol2, grid2))
