@@ -96,10 +96,11 @@ __global__ void __launch_bounds__(kThreads) k_sampler_fwd_packed(const SamplerAr
 }
 
 // resident CTAs per SM the single-channel float backward is compiled for (register cap 65536 / (256 * n)): 6 -> 40
-// registers, 5 -> 48, 4 -> 64.  Swept again in round 2 with the per-warp quad path in the body
-// (profiles/r02_bwd_launch_bounds.md).
+// registers and 24-byte spills (6 STL + 6 LDL), 5 -> 48 registers, no spills, 4 -> 56.  Swept again in round 2 with the
+// per-warp quad path in the body (profiles/r02_bwd_launch_bounds.md): identity field 187.0 / 187.5 / 202.4 us, jittered
+// cage 468 / 467 / 474 us, uniformly random 682 / 662 / 661 us at 6 / 5 / 4 -- 5 is as fast as 6 and spill-free.
 #ifndef VOLSTN_BWD_CTAS
-#define VOLSTN_BWD_CTAS 6
+#define VOLSTN_BWD_CTAS 5
 #endif
 template <typename real, int CT, int G, int VPT, bool ONLY_GRID, bool ONLY_VOL>
 __global__ void __launch_bounds__(kThreads, (CT == 1 && sizeof(real) == 4) ? VOLSTN_BWD_CTAS : 1) k_sampler_bwd_packed(const SamplerArgs<real> a) {

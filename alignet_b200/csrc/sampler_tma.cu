@@ -32,7 +32,10 @@ namespace {
 
 constexpr int kTB = 8;                       // output brick edge
 constexpr int kTmaThreads = 256;             // two voxels per thread
-constexpr int kBoxX = 16, kBoxY = 16, kBoxZ = 16;
+// The box must START on a 16-byte boundary of the innermost dimension (x a multiple of 4 floats): an unaligned start
+// coordinate raises an illegal-instruction fault on the B200 (tools/probe/tma_probe*.cu, profiles/r02_tma.md), so the box
+// is 4 cells longer in x than in y and z to absorb the alignment.
+constexpr int kBoxX = 20, kBoxY = 16, kBoxZ = 16;
 constexpr int kBoxCells = kBoxX * kBoxY * kBoxZ;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArg
   BrickVoxel v[2];
   brick_setup<G, 2>(p, v, s_meta, b, bx, by, bz);
   __syncthreads();
-  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2];
+  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2] & ~3;  // 16-byte aligned start (floor, also below zero)
   const bool staged = !s_meta[6] && s_meta[3] - z_lo + 2 <= kBoxZ && s_meta[4] - y_lo + 2 <= kBoxY && s_meta[5] - x_lo + 2 <= kBoxX;
   float *ob = a.out + (size_t)b * a.n32;
   if (staged) {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
     if ((threadIdx.x & 31) == 0 && go_abs) atomicMax(reinterpret_cast<unsigned *>(&s_meta[7]), go_abs);
   }
   __syncthreads();
-  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2];
+  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2] & ~3;  // 16-byte aligned start (floor, also below zero)
   const unsigned go_max = (unsigned)s_meta[7];
   const bool staged = !s_meta[6] && go_max < 0x7f800000u && s_meta[3] - z_lo + 2 <= kBoxZ && s_meta[4] - y_lo + 2 <= kBoxY &&
                       s_meta[5] - x_lo + 2 <= kBoxX;
