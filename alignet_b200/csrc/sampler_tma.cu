@@ -9,8 +9,9 @@
 //     of the brick's corner cells small: about (8 |J| + 2)^3 cells for a field with Jacobian J;
 //   * the CTA reduces the box [min i0, max i0 + 1] of its corner indices (REDUX + six shared atomics) and ONE thread
 //     issues ONE `cp.async.bulk.tensor.4d` (a BX x BY x BZ x 1 box of the B x D x H x W volume) into shared memory.
-//     TMA's out-of-bounds ZERO FILL is exactly the reference's padding rule (an out-of-bounds corner reads as 0,
-//     ...c:542-564), so the staged path needs no bounds predicates at all -- any finite coordinate is handled;
+//     TMA's out-of-bounds ZERO FILL is the reference's padding rule (an out-of-bounds corner reads as 0,
+//     ...c:542-564) beyond the high faces; below zero the box is clamped (a TMA reduction faults on a negative start
+//     coordinate, measured) and the corner predicates of the exact tier do the rest -- any finite coordinate is handled;
 //   * the eight corners are then shared-memory loads, and the arithmetic is the direct kernels' (sampler.cuh:
 //     corner_weights, the reference's summation order): `out` and gradGrid keep the reference's bits;
 //   * backward: gradVol is privatised in a second shared-memory box in fixed point (native ATOMS.ADD; a float
@@ -35,7 +36,30 @@ constexpr int kTmaThreads = 256;             // two voxels per thread
 // The box must START on a 16-byte boundary of the innermost dimension (x a multiple of 4 floats): an unaligned start
 // coordinate raises an illegal-instruction fault on the B200 (tools/probe/tma_probe*.cu, profiles/r02_tma.md), so the box
 // is 4 cells longer in x than in y and z to absorb the alignment.
-constexpr int kBoxX = 20, kBoxY = 16, kBoxZ = 16;
+#ifndef VOLSTN_TMA_BOX
+#define VOLSTN_TMA_BOX 16
+#endif
+#ifndef VOLSTN_TMA_CTAS_FWD
+#define VOLSTN_TMA_CTAS_FWD 4
+#endif
+#ifndef VOLSTN_TMA_CTAS_BWD
+#define VOLSTN_TMA_CTAS_BWD 3
+#endif
+constexpr int kBoxX = VOLSTN_TMA_BOX + 4, kBoxY = VOLSTN_TMA_BOX, kBoxZ = VOLSTN_TMA_BOX;
+// ... and a SMALL box for bricks of fields that barely shear (identity-like fields: 8 + 2 cells per axis): what a brick
+// costs is, first of all, the bytes its boxes move (a 24^3 box: 4x the time, profiles/r02_tma.md), so each brick takes
+// the smallest of the two boxes that holds it.  A tensor map fixes its box size: two maps per tensor.
+// MEASURED AND SWITCHED OFF (profiles/r02_tma.md): the identity field's backward gains 10 % (322 -> 291 us) but every
+// forward and the rotations lose 5-20 % -- with two box sizes the box pitches are run-time values and the eight corner
+// addresses of a voxel cost integer multiplies.  VOLSTN_TMA_DUAL = 1 re-enables it.
+#ifndef VOLSTN_TMA_DUAL
+#define VOLSTN_TMA_DUAL 0
+#endif
+#ifndef VOLSTN_TMA_SMALL
+#define VOLSTN_TMA_SMALL 12
+#endif
+constexpr int kSmX = VOLSTN_TMA_SMALL + 4, kSmY = VOLSTN_TMA_SMALL, kSmZ = VOLSTN_TMA_SMALL;
+constexpr int kSmCells = kSmX * kSmY * kSmZ;
 constexpr int kBoxCells = kBoxX * kBoxY * kBoxZ;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -145,10 +169,12 @@ __device__ __forceinline__ bool brick_setup(const TmaArgs &p, BrickVoxel (&v)[VP
 // forward
 // =============================================================================================
 template <int G>
-__global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArgs p, const __grid_constant__ CUtensorMap vmap) {
+__global__ void __launch_bounds__(kTmaThreads, VOLSTN_TMA_CTAS_FWD) k_sampler_fwd_tma(const TmaArgs p, const __grid_constant__ CUtensorMap vmap,
+                                                                                        const __grid_constant__ CUtensorMap vmap_s) {
   using E = Ex<float>;
   const SamplerArgs<float> &a = p.s;
-  __shared__ __align__(128) float s_box[kBoxCells];
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  float *s_box = reinterpret_cast<float *>(tma_smem);
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_meta[8];
   const int bx = blockIdx.x, by = blockIdx.y;
@@ -162,13 +188,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArg
   BrickVoxel v[2];
   brick_setup<G, 2>(p, v, s_meta, b, bx, by, bz);
   __syncthreads();
-  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2] & ~3;  // 16-byte aligned start (floor, also below zero)
-  const bool staged = !s_meta[6] && s_meta[3] - z_lo + 2 <= kBoxZ && s_meta[4] - y_lo + 2 <= kBoxY && s_meta[5] - x_lo + 2 <= kBoxX;
+  // box origin: the low corner cells, clamped at 0 (cells below zero are out of bounds: predicated away, never staged)
+  // and, in x, aligned down to 16 bytes
+  const int z_lo = max(s_meta[0], 0), y_lo = max(s_meta[1], 0), x_lo = max(s_meta[2], 0) & ~3;
+  const int ez = s_meta[3] - z_lo + 2, ey = s_meta[4] - y_lo + 2, ex = s_meta[5] - x_lo + 2;  // cells the brick touches
+  const bool staged = !s_meta[6] && ez <= kBoxZ && ey <= kBoxY && ex <= kBoxX;
+  const bool small = VOLSTN_TMA_DUAL && ez <= kSmZ && ey <= kSmY && ex <= kSmX;
+  const int pX = small ? kSmX : kBoxX, pXY = small ? kSmX * kSmY : kBoxX * kBoxY;  // pitches of the staged box
   float *ob = a.out + (size_t)b * a.n32;
   if (staged) {
     if (threadIdx.x == 0) {
-      mbar_expect_tx(&s_bar, kBoxCells * 4);
-      tma_load_4d(s_box, &vmap, &s_bar, x_lo, y_lo, z_lo, (int)b);
+      mbar_expect_tx(&s_bar, (small ? kSmCells : kBoxCells) * 4);
+      tma_load_4d(s_box, small ? &vmap_s : &vmap, &s_bar, x_lo, y_lo, z_lo, (int)b);
     }
     // the corner weights do not need the data: computed while the box is in flight
     float cw[2][8];
@@ -176,7 +207,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArg
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       v[q].su.corner_weights(cw[q]);
-      base[q] = ((v[q].su.z0 - z_lo) * kBoxY + (v[q].su.y0 - y_lo)) * kBoxX + (v[q].su.x0 - x_lo);
+      base[q] = (v[q].su.z0 - z_lo) * pXY + (v[q].su.y0 - y_lo) * pX + (v[q].su.x0 - x_lo);
     }
     mbar_wait(&s_bar, 0);
 #pragma unroll
@@ -185,7 +216,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArg
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) {
         const int k = (G == 4) ? order_xyz(jj) : order_zxy(jj);  // ...c:566-573 / ...c:149-156
-        const float val = s_box[base[q] + (k & 1) + ((k >> 1) & 1) * kBoxX + (k >> 2) * kBoxX * kBoxY];  // 0 outside (TMA fill)
+        // out-of-bounds corners read as 0 (...c:531-564): beyond the high faces TMA has filled zeros, below zero the
+        // cell is not in the box at all
+        const float val = v[q].su.in(k) ? s_box[base[q] + (k & 1) + ((k >> 1) & 1) * pX + (k >> 2) * pXY] : 0.f;
         const float term = E::mul(cw[q][k], val);
         acc = jj ? E::add(acc, term) : term;
       }
@@ -204,12 +237,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_sampler_fwd_tma(const TmaArg
 // backward: gradGrid (bit-exact) + gradVol privatised in shared memory, flushed by one TMA reduction
 // =============================================================================================
 template <int G, bool ONLY_GRID>
-__global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArgs p, const __grid_constant__ CUtensorMap vmap,
-                                                                   const __grid_constant__ CUtensorMap gmap) {
+__global__ void __launch_bounds__(kTmaThreads, VOLSTN_TMA_CTAS_BWD) k_sampler_bwd_tma(const TmaArgs p, const __grid_constant__ CUtensorMap vmap,
+                                                                   const __grid_constant__ CUtensorMap gmap,
+                                                                   const __grid_constant__ CUtensorMap vmap_s,
+                                                                   const __grid_constant__ CUtensorMap gmap_s) {
   using E = Ex<float>;
   const SamplerArgs<float> &a = p.s;
-  __shared__ __align__(128) float s_box[kBoxCells];
-  __shared__ __align__(128) int s_acc[ONLY_GRID ? 32 : kBoxCells];
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  float *s_box = reinterpret_cast<float *>(tma_smem);
+  int *s_acc = reinterpret_cast<int *>(tma_smem + (size_t)kBoxCells * 4);  // only with the gradVol scatter
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_meta[8];
   const int bx = blockIdx.x, by = blockIdx.y;
@@ -219,9 +255,6 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
   else if (threadIdx.x < 6) s_meta[threadIdx.x] = INT32_MIN;
   else if (threadIdx.x < 8) s_meta[threadIdx.x] = 0;
   if (threadIdx.x == 32) mbar_init(&s_bar, 1);
-  if constexpr (!ONLY_GRID) {
-    for (int i = threadIdx.x; i < kBoxCells / 4; i += kTmaThreads) reinterpret_cast<int4 *>(s_acc)[i] = make_int4(0, 0, 0, 0);
-  }
   __syncthreads();
   BrickVoxel v[2];
   brick_setup<G, 2>(p, v, s_meta, b, bx, by, bz);
@@ -239,10 +272,15 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
     if ((threadIdx.x & 31) == 0 && go_abs) atomicMax(reinterpret_cast<unsigned *>(&s_meta[7]), go_abs);
   }
   __syncthreads();
-  const int z_lo = s_meta[0], y_lo = s_meta[1], x_lo = s_meta[2] & ~3;  // 16-byte aligned start (floor, also below zero)
+  // box origin clamped at 0 and 16-byte aligned in x: a TMA REDUCTION with a negative start coordinate faults (a load
+  // does not; tools/probe/tma_probe.cu), and cells below zero never receive anything anyway
+  const int z_lo = max(s_meta[0], 0), y_lo = max(s_meta[1], 0), x_lo = max(s_meta[2], 0) & ~3;
   const unsigned go_max = (unsigned)s_meta[7];
-  const bool staged = !s_meta[6] && go_max < 0x7f800000u && s_meta[3] - z_lo + 2 <= kBoxZ && s_meta[4] - y_lo + 2 <= kBoxY &&
-                      s_meta[5] - x_lo + 2 <= kBoxX;
+  const int ez = s_meta[3] - z_lo + 2, ey = s_meta[4] - y_lo + 2, ex = s_meta[5] - x_lo + 2;  // cells the brick touches
+  const bool staged = !s_meta[6] && go_max < 0x7f800000u && ez <= kBoxZ && ey <= kBoxY && ex <= kBoxX;
+  const bool small = VOLSTN_TMA_DUAL && ez <= kSmZ && ey <= kSmY && ex <= kSmX;
+  const int pX = small ? kSmX : kBoxX, pXY = small ? kSmX * kSmY : kBoxX * kBoxY;
+  const int cells = small ? kSmCells : kBoxCells;
   float *ggb = a.ggrid + sb * G;
   const float *vb = a.vol + (size_t)b * a.vs32;
   const int sH = a.iW, sD = a.iH * a.iW;
@@ -255,8 +293,12 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
     return;
   }
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&s_bar, kBoxCells * 4);
-    tma_load_4d(s_box, &vmap, &s_bar, x_lo, y_lo, z_lo, (int)b);
+    mbar_expect_tx(&s_bar, cells * 4);
+    tma_load_4d(s_box, small ? &vmap_s : &vmap, &s_bar, x_lo, y_lo, z_lo, (int)b);
+  }
+  if constexpr (!ONLY_GRID) {  // the privatised gradVol box of this brick's size, zeroed while the volume box is in flight
+    for (int i = threadIdx.x; i < cells / 4; i += kTmaThreads) reinterpret_cast<int4 *>(s_acc)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
   }
   // fixed point for the privatised gradVol: 2^20 steps up to the power of two above max |gradOut| of the brick, so that
   // one contribution (|w| <= 1) is rounded by at most 2^-21 of that maximum and the 512 voxels of a brick cannot overflow
@@ -268,7 +310,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     v[q].su.corner_weights(cw[q]);
-    base[q] = ((v[q].su.z0 - z_lo) * kBoxY + (v[q].su.y0 - y_lo)) * kBoxX + (v[q].su.x0 - x_lo);
+    base[q] = (v[q].su.z0 - z_lo) * pXY + (v[q].su.y0 - y_lo) * pX + (v[q].su.x0 - x_lo);
   }
   if constexpr (!ONLY_GRID) {
     // the scatter does not need the staged volume either
@@ -280,7 +322,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
           // ...c:737, then round(c * scale) without a conversion instruction (|c * scale| < 2^21: adding 1.5 * 2^23 leaves
           // the integer in the mantissa)
           const int qv = __float_as_int(__fmaf_rn(E::mul(cw[q][k], go[q]), scale, 12582912.0f)) - 0x4B400000;
-          if (qv) atomicAdd(&s_acc[base[q] + (k & 1) + ((k >> 1) & 1) * kBoxX + (k >> 2) * kBoxX * kBoxY], qv);
+          if (qv && v[q].su.in(k)) atomicAdd(&s_acc[base[q] + (k & 1) + ((k >> 1) & 1) * pX + (k >> 2) * pXY], qv);
         }
       }
     }
@@ -291,9 +333,10 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
     float dot[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float val = s_box[base[q] + (k & 1) + ((k >> 1) & 1) * kBoxX + (k >> 2) * kBoxX * kBoxY];
-      // dot = 0 + v * go (...c:736); an out-of-bounds corner stays 0 and never sees go
-      dot[k] = v[q].su.in(k) ? E::add(0.f, E::mul(val, go[q])) : 0.f;
+      // dot = 0 + v * go (...c:736); an out-of-bounds corner stays 0, never sees go and is never read
+      const bool in = v[q].su.in(k);
+      const float val = in ? s_box[base[q] + (k & 1) + ((k >> 1) & 1) * pX + (k >> 2) * pXY] : 0.f;
+      dot[k] = in ? E::add(0.f, E::mul(val, go[q])) : 0.f;
     }
     float gz, gy, gx;
     grad_grid_from_dots<float>(dot, v[q].su, a, gz, gy, gx);
@@ -302,7 +345,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
   if constexpr (!ONLY_GRID) {
     __syncthreads();
     // fixed point -> float in place, then ONE box reduction into gradVol (cells outside the volume are dropped)
-    for (int i = threadIdx.x; i < kBoxCells / 4; i += kTmaThreads) {
+    for (int i = threadIdx.x; i < cells / 4; i += kTmaThreads) {
       const int4 qv = reinterpret_cast<const int4 *>(s_acc)[i];
       reinterpret_cast<float4 *>(s_acc)[i] =
           make_float4((float)qv.x * inv_scale, (float)qv.y * inv_scale, (float)qv.z * inv_scale, (float)qv.w * inv_scale);
@@ -310,7 +353,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k_sampler_bwd_tma(const TmaArg
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
-      tma_reduce_add_4d(&gmap, s_acc, x_lo, y_lo, z_lo, (int)b);
+      tma_reduce_add_4d(small ? &gmap_s : &gmap, s_acc, x_lo, y_lo, z_lo, (int)b);
       tma_commit_and_wait_read();  // shared memory must stay valid until the engine has read it
     }
   }
@@ -341,15 +384,22 @@ EncodeTiledFn encode_tiled() {
 }
 
 // B x D x H x W float tensor (C = 1, contiguous) as a rank-4 tiled map with a kBoxX x kBoxY x kBoxZ x 1 box
-bool make_map(CUtensorMap *m, const float *base, int B, int D, int H, int W) {
+bool make_map(CUtensorMap *m, const float *base, int B, int D, int H, int W, bool small_box) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * D * 4};
-  const cuuint32_t box[4] = {kBoxX, kBoxY, kBoxZ, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)(small_box ? kSmX : kBoxX), (cuuint32_t)(small_box ? kSmY : kBoxY),
+                             (cuuint32_t)(small_box ? kSmZ : kBoxZ), 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename K>
+int big_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) VOLSTN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return VOLSTN_OK;
 }
 
 bool fill_bricks(TmaArgs &p, const SamplerArgs<float> &a) {
@@ -370,35 +420,50 @@ bool tma_supported(const SamplerArgs<float> &a, const float *gvol) {
 
 int launch_fwd_tma(const SamplerArgs<float> &a, int G, cudaStream_t st) {
   TmaArgs p;
-  CUtensorMap vmap;
-  if (!fill_bricks(p, a) || !make_map(&vmap, a.vol, a.B, a.iD, a.iH, a.iW)) return VOLSTN_ERR_UNSUPPORTED;
+  CUtensorMap vmap, vmap_s;
+  if (!fill_bricks(p, a) || !make_map(&vmap, a.vol, a.B, a.iD, a.iH, a.iW, false) || !make_map(&vmap_s, a.vol, a.B, a.iD, a.iH, a.iW, true))
+    return VOLSTN_ERR_UNSUPPORTED;
   const dim3 grid(p.nbx, p.nby, (unsigned)(p.nbz * a.B));
-  if (G == 4)
-    k_sampler_fwd_tma<4><<<grid, kTmaThreads, 0, st>>>(p, vmap);
-  else
-    k_sampler_fwd_tma<3><<<grid, kTmaThreads, 0, st>>>(p, vmap);
+  const size_t smem = (size_t)kBoxCells * 4;
+  int rc;
+  if (G == 4) {
+    if ((rc = big_smem(k_sampler_fwd_tma<4>, smem))) return rc;
+    k_sampler_fwd_tma<4><<<grid, kTmaThreads, smem, st>>>(p, vmap, vmap_s);
+  } else {
+    if ((rc = big_smem(k_sampler_fwd_tma<3>, smem))) return rc;
+    k_sampler_fwd_tma<3><<<grid, kTmaThreads, smem, st>>>(p, vmap, vmap_s);
+  }
   return after_launch();
 }
 
 int launch_bwd_tma(const SamplerArgs<float> &a, int G, bool only_grid, cudaStream_t st) {
   TmaArgs p;
-  CUtensorMap vmap, gmap;
-  if (!fill_bricks(p, a) || !make_map(&vmap, a.vol, a.B, a.iD, a.iH, a.iW)) return VOLSTN_ERR_UNSUPPORTED;
+  CUtensorMap vmap, gmap, vmap_s, gmap_s;
+  if (!fill_bricks(p, a) || !make_map(&vmap, a.vol, a.B, a.iD, a.iH, a.iW, false) || !make_map(&vmap_s, a.vol, a.B, a.iD, a.iH, a.iW, true))
+    return VOLSTN_ERR_UNSUPPORTED;
   if (only_grid)
-    gmap = vmap;
-  else if (!make_map(&gmap, a.gvol, a.B, a.iD, a.iH, a.iW))
+    gmap = vmap, gmap_s = vmap_s;
+  else if (!make_map(&gmap, a.gvol, a.B, a.iD, a.iH, a.iW, false) || !make_map(&gmap_s, a.gvol, a.B, a.iD, a.iH, a.iW, true))
     return VOLSTN_ERR_UNSUPPORTED;
   const dim3 grid(p.nbx, p.nby, (unsigned)(p.nbz * a.B));
+  const size_t smem = (size_t)kBoxCells * 4 * (only_grid ? 1 : 2);
+  int rc;
   if (G == 4) {
-    if (only_grid)
-      k_sampler_bwd_tma<4, true><<<grid, kTmaThreads, 0, st>>>(p, vmap, gmap);
-    else
-      k_sampler_bwd_tma<4, false><<<grid, kTmaThreads, 0, st>>>(p, vmap, gmap);
+    if (only_grid) {
+      if ((rc = big_smem(k_sampler_bwd_tma<4, true>, smem))) return rc;
+      k_sampler_bwd_tma<4, true><<<grid, kTmaThreads, smem, st>>>(p, vmap, gmap, vmap_s, gmap_s);
+    } else {
+      if ((rc = big_smem(k_sampler_bwd_tma<4, false>, smem))) return rc;
+      k_sampler_bwd_tma<4, false><<<grid, kTmaThreads, smem, st>>>(p, vmap, gmap, vmap_s, gmap_s);
+    }
   } else {
-    if (only_grid)
-      k_sampler_bwd_tma<3, true><<<grid, kTmaThreads, 0, st>>>(p, vmap, gmap);
-    else
-      k_sampler_bwd_tma<3, false><<<grid, kTmaThreads, 0, st>>>(p, vmap, gmap);
+    if (only_grid) {
+      if ((rc = big_smem(k_sampler_bwd_tma<3, true>, smem))) return rc;
+      k_sampler_bwd_tma<3, true><<<grid, kTmaThreads, smem, st>>>(p, vmap, gmap, vmap_s, gmap_s);
+    } else {
+      if ((rc = big_smem(k_sampler_bwd_tma<3, false>, smem))) return rc;
+      k_sampler_bwd_tma<3, false><<<grid, kTmaThreads, smem, st>>>(p, vmap, gmap, vmap_s, gmap_s);
+    }
   }
   return after_launch();
 }

@@ -1,9 +1,9 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02f_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02f_pytest.log
-tail -15 gpurun_out/r02f_pytest.log
-timeout 300 python tools/kbench.py --grids g1,g2,g3,g5 --algos 0,6 --iters 20 > gpurun_out/r02f_kbench_tma.txt 2>&1
-timeout 300 python tools/kbench.py --grids g2,g5 --algos 0,6,2 --iters 10 --size 128 --batch 8 >> gpurun_out/r02f_kbench_tma.txt 2>&1
-cat gpurun_out/r02f_kbench_tma.txt
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r02f_bench.json 2> gpurun_out/r02f_bench.err; echo "bench rc=$?"
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02j_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02j_pytest.log
+tail -15 gpurun_out/r02j_pytest.log
+timeout 300 python tools/kbench.py --grids g1,g2,g3,g5 --algos 0,6 --iters 20 > gpurun_out/r02j_kbench_tma.txt 2>&1
+timeout 300 python tools/kbench.py --grids g2,g5 --algos 0,6,2 --iters 10 --size 128 --batch 8 >> gpurun_out/r02j_kbench_tma.txt 2>&1
+cat gpurun_out/r02j_kbench_tma.txt
+
