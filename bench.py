@@ -557,9 +557,17 @@ def run_e2e(a, torch, dist, vnn, _abi, shard, vol_h, grid_h, go_h, V, n_gpus, di
             dist.all_gather(allr, tt)
             per_rank = [[round(float(x), 2) for x in r] for r in allr]
         lb_ms = max(h2d / up_gbs, d2h / down_gbs) / 1e6
+        # the step keeps both directions busy most of the time: every byte of it over this rank's link at the rate the link
+        # carries when both directions run (all ranks measured at the same time) -- the ceiling the platform sets
+        duplex_ms = (h2d + d2h) / (2 * both_gbs) / 1e6
+        agg_both = 2 * (sum(r[2] for r in per_rank) if per_rank else both_gbs)
         link = {"h2d_gbs": up_gbs, "d2h_gbs": down_gbs, "each_way_gbs_when_both_run": both_gbs,
                 "per_rank_h2d_d2h_both_gbs": per_rank, "aggregate_h2d_gbs": sum(r[0] for r in per_rank) if per_rank else up_gbs,
                 "aggregate_d2h_gbs": sum(r[1] for r in per_rank) if per_rank else down_gbs,
+                "aggregate_both_directions_gbs": agg_both,
+                "step_gbs_all_ranks_both_directions": (h2d + d2h) * n_gpus / sec / 1e9,
+                "frac_of_aggregate_duplex_ceiling": (h2d + d2h) * n_gpus / sec / 1e9 / agg_both,
+                "duplex_bound_ms_per_step": duplex_ms,
                 "lower_bound_ms_per_step": lb_ms, "frac_of_link_bound": lb_ms / (sec * 1e3),
                 "numa_node_of_gpu": int(lib.volstn_b200_host_numa_node(local)),
                 "note": "all ranks copy at the same time; the bound is max(upload bytes / h2d rate, download bytes / d2h rate) of this rank's link as measured with every other rank's link busy"}
