@@ -203,3 +203,25 @@ def test_compute_iou_reference_grouping_is_modulo_batch():
     assert abs(per_sample - ref) > 1e-6                      # the two groupings are different numbers
     got = float(vnn.computeIOU(torch.from_numpy(pred), torch.from_numpy(tgt)))
     assert abs(got - ref) <= 1e-15
+
+
+def test_gridgen_restatement_agrees_with_aten_bmm():
+    """nn.VolumetricGridGenerator is Lua over torch.bmm / baddbmm (VolumetricGridGenerator.lua:58-60, 79-82) -- Torch7 TH,
+    not vendored, parity UNPINNED.  ATen's CPU bmm / baddbmm are TH's direct descendants (same BLAS call underneath): the
+    numpy restatement must agree with the Lua module's own sequence of operations executed on them."""
+    import torch
+    rng = np.random.default_rng(31)
+    B, D, H, W = 3, 5, 6, 7
+    T = rng.standard_normal((B, 4, 4)).astype(np.float32)
+    base = torch.from_numpy(oracle.gridgen_base(D, H, W))                            # lua:12-23
+    batch_grid = base.view(1, D, H, W, 4).repeat(B, 1, 1, 1, 1)                       # lua:50-55
+    out = torch.bmm(batch_grid.view(B, D * H * W, 4), torch.from_numpy(T).transpose(1, 2))   # lua:58-60
+    ref = oracle.gridgen_forward(T, D, H, W)
+    assert np.max(np.abs(out.view(B, D, H, W, 4).numpy() - ref)) <= 1e-6
+    gg = rng.standard_normal((B, D, H, W, 4)).astype(np.float32)
+    grad_t = torch.zeros(B, 4, 4).baddbmm(torch.from_numpy(gg).view(B, D * H * W, 4).transpose(1, 2), batch_grid.view(B, D * H * W, 4))  # lua:79-82
+    assert max_rel_np(grad_t.numpy(), oracle.gridgen_backward(gg)) <= 1e-5
+
+
+def max_rel_np(a, b):
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / max(1e-30, float(np.max(np.abs(b)))))
