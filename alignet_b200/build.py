@@ -22,8 +22,8 @@ BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libvolstn_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "sampler_tma.cu", "rowwarp.cu", "fused_api.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
-HEADERS = ["volstn_common.cuh", "sampler.cuh", "rowwarp.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
+SOURCES = ["abi.cu", "sampler.cu", "sampler_tile.cu", "sampler_tma.cu", "rowwarp.cu", "cagebrick.cu", "fused_api.cu", "gridgen.cu", "cumsum.cu", "host_api.cu"]
+HEADERS = ["volstn_common.cuh", "sampler.cuh", "rowwarp.cuh", "cagebrick.cuh", "volstn_internal.h", os.path.join(INCLUDE, "volstn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

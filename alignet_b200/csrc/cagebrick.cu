@@ -1,0 +1,485 @@
+// cagebrick.cu -- BRICK kernels: ALIGNet's cage warp (models/alignet_2d.lua:136-147 lifted to 3-D) for
+// its training case -- contiguous single-channel tensors -- in the separable arithmetic of VOLSTN_FAST_ARITH.
+//
+// The row kernels (rowwarp.cu) spend two thirds of their 596 warp instructions per 32 voxels on addresses, predicates
+// and shared-memory traffic: every voxel re-derives its cage cell, reloads eight cage corners from shared
+// memory and stages its gradient for a per-row segment sum.  The mapping here removes that work instead of making the
+// arithmetic cheaper:
+//
+//   * a WARP owns a brick: one 32-wide x slot of the rows of ONE cage cell in y and (a part of) one cage cell in z.  A
+//     lane's x never changes, so its cage column (ix, wx) is a register constant, and the cell (kz, ky) is constant for
+//     the whole task: the twelve x-interpolated cage values  P[j][k][c] = wx.C[c][kz+k][ky+j][ix] + wx'.C[..][ix+1]  are
+//     formed ONCE per task, folded along z once per z (R[j][c], already in voxel units of the source volume) and a
+//     voxel's three sampling coordinates are two FMAs each;
+//   * the gradient takes the same road back: per voxel  S[j][c] += wy_j . (go . d out/d coord_c)  (six FMAs), per z
+//     A[j][k][c] += wz_k . S[j][c], and per TASK one segmented warp reduction over the lanes that share a cage column and
+//     one red.global per (cell corner, channel) -- no shared memory, no staging, no per-row sums;
+//   * the trilinear value and its three coordinate derivatives come from the seven lerps of the separable form
+//     (22 flops instead of the reference's 8 + 7 and 40 + 21);
+//   * two tiers per warp and row: STRICT (every corner of every lane inside the volume: conversion-free floor, no
+//     predicates) and GENERAL (coordinates clamped to [-2, size + 1] and shifted by 2 so that the same floor trick
+//     applies; corners outside the volume are predicated off and read as the reference's zero padding,
+//     ...c:542-564, with zero value AND zero derivative beyond one voxel outside).
+//
+// Same mathematics as the reference chain, different rounding: these kernels exist only behind VOLSTN_FAST_ARITH
+// (include/volstn_b200.h), whose guarantees are measured in tests/test_gpu_rowwarp.py::test_fast_arith_*.
+#include <cstdlib>
+#include <cstring>
+
+#include "cagebrick.cuh"
+
+namespace volstn {
+
+constexpr int kBrickThreads = 256;
+constexpr int kBrickWarps = kBrickThreads / 32;
+
+// (float)(-1 + k/(n-1)*2) in double: VolumetricGridGenerator.lua:17-19 (as rowwarp.cu::row_base_coord)
+__device__ __forceinline__ float brick_base_coord(int k, int n) {
+  return (float)(-1.0 + (double)k / (double)(n - 1) * 2.0);
+}
+
+struct BrickSmem {
+  float2 *wz, *wy, *wx;  // (weight of the low cage corner, weight of the high one) per output position
+  int *iz, *iy, *ix;     // low cage corner per output position, remapped so that the high corner exists (see brick_fill)
+  int *zs, *ys;          // first position of z / y unit k (k = 0 .. units)
+  float *lane;           // per-thread slots: 12 folded cage values, 12 gradient accumulators ([slot][thread])
+};
+
+__host__ __device__ inline int brick_units(int cn) { return cn > 1 ? cn - 1 : 1; }
+
+__host__ __device__ inline size_t brick_smem_bytes(const BrickArgs &a) {
+  const size_t axes = (size_t)a.oD + a.oH + a.oW;
+  return 24 * 256 * 4 + axes * 12 + (size_t)(brick_units(a.cD) + brick_units(a.cH) + 2) * 4 + 16;
+}
+
+__device__ __forceinline__ void brick_fill(BrickSmem &m, unsigned char *raw, const BrickArgs &a) {
+  const int oD = a.oD, oH = a.oH, oW = a.oW, axes = oD + oH + oW;
+  m.lane = reinterpret_cast<float *>(raw);
+  m.wz = reinterpret_cast<float2 *>(raw + 24 * 256 * 4);
+  m.wy = m.wz + oD;
+  m.wx = m.wy + oH;
+  m.iz = reinterpret_cast<int *>(m.wz + axes);
+  m.iy = m.iz + oD;
+  m.ix = m.iy + oH;
+  m.zs = m.iz + axes;
+  m.ys = m.zs + brick_units(a.cD) + 1;
+  // the sampler's own set-up (...c:507-517) of the identity coordinate of every axis position.  The identity coordinate
+  // never leaves [0, cn - 1]; its last position sits ON the last cage node (i0 = cn - 1, low weight 1, high corner in
+  // the zero padding): there the cell below with weights (0, 1) is the same value, and every position of an axis then
+  // has its high corner inside the cage.  A one-node axis keeps (i0 = 0, high weight 0).
+  for (int i = threadIdx.x; i < axes; i += blockDim.x) {
+    int k, n, cn;
+    if (i < oD)
+      k = i, n = oD, cn = a.cD;
+    else if (i < oD + oH)
+      k = i - oD, n = oH, cn = a.cH;
+    else
+      k = i - oD - oH, n = oW, cn = a.cW;
+    int i0;
+    float w;
+    axis_setup<float>(brick_base_coord(k, n), (float)(cn - 1), i0, w);
+    float2 ww = make_float2(w, 1.0f - w);
+    if (cn == 1)
+      i0 = 0, ww = make_float2(w, 0.0f);
+    else if (i0 >= cn - 1)
+      i0 = cn - 2, ww = make_float2(1.0f - w, w);  // w == 1 there: weights (0, 1) on the cell below
+    else if (i0 < 0)
+      i0 = 0, ww = make_float2(1.0f, 0.0f);        // cannot happen (the coordinate is >= 0); keeps the indices safe
+    m.wz[i] = ww;  // wz / wy / wx and iz / iy / ix are consecutive
+    m.iz[i] = i0;
+  }
+  __syncthreads();
+  // unit k of an axis = the positions whose (remapped) low corner is k: a contiguous, possibly empty range
+  const int nzu = brick_units(a.cD), nyu = brick_units(a.cH);
+  for (int i = threadIdx.x; i <= nzu + nyu + 1; i += blockDim.x) {
+    const bool isz = i <= nzu;
+    const int k = isz ? i : i - nzu - 1, n = isz ? oD : oH, units = isz ? nzu : nyu;
+    const int *tab = isz ? m.iz : m.iy;
+    int first = n;
+    if (k < units) {
+      first = 0;
+      while (first < n && tab[first] < k) first++;
+    }
+    (isz ? m.zs : m.ys)[k] = first;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// NR consecutive rows of the task: coordinates -> ONE tier vote -> all gathers in flight -> values, derivatives, sinks
+// ---------------------------------------------------------------------------------------------
+struct BrickLane {
+  float S[2][3];  // gradient of R[j][c], accumulated over the rows of one z
+  float lsum;     // SmoothL1 terms of this lane (float: at most a few thousand terms of O(1) per task)
+  int ni, nu;     // IoU counts of this lane
+};
+
+// MODE: 0 = forward (store out), 1 = backward from gradOut, 2 = training step (SmoothL1 + IoU + backward, optional out)
+// VS: 0 = run-time strides of the source volume, else iW = iH = VS (row and plane offsets are immediates of the loads)
+// The kernels are LATENCY-bound, not issue-bound (first version, one vote and one row at a time: 145 us forward at
+// 64^3 x 64 with ~70 instructions per voxel-warp): the rows of a trip share one vote so that all their gathers are in
+// flight together, and the target / gradOut element of every row is requested before the vote.
+template <int MODE, bool GV, int VS, int NR, bool GENERAL>
+__device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__restrict__ vb, const float (&c)[NR][3],
+                                           const float2 (&wy)[NR], const float (&tg)[NR], long long e0, bool valid,
+                                           BrickLane &L) {
+  const int sH = VS ? VS : a.iW, sD = VS ? VS * VS : a.iH * a.iW;
+  float f[NR][3];
+  const float *p0[NR];
+  bool zl[NR], zh[NR], yl[NR], yh[NR], xl[NR], xh[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    int off;
+    if constexpr (GENERAL) {
+      // clamp to [-2, size + 1] (NaN -> -2), shift by 2: t in [0, size + 3], floor by the 2^23 trick; corner i0 = j - 2
+      const float tz = __fadd_rn(fminf(fmaxf(c[r][0], -2.0f), a.cmz), 2.0f);
+      const float ty = __fadd_rn(fminf(fmaxf(c[r][1], -2.0f), a.cmy), 2.0f);
+      const float tx = __fadd_rn(fminf(fmaxf(c[r][2], -2.0f), a.cmx), 2.0f);
+      const float rz = __fadd_rd(tz, 8388608.0f), ry = __fadd_rd(ty, 8388608.0f), rx = __fadd_rd(tx, 8388608.0f);
+      f[r][0] = __fsub_rn(tz, __fsub_rn(rz, 8388608.0f));
+      f[r][1] = __fsub_rn(ty, __fsub_rn(ry, 8388608.0f));
+      f[r][2] = __fsub_rn(tx, __fsub_rn(rx, 8388608.0f));
+      // low corner inside: 2 <= t < size + 2; high corner inside: 1 <= t < size + 1
+      zl[r] = tz >= 2.0f && tz < a.lz, zh[r] = tz >= 1.0f && tz < a.cmz;
+      yl[r] = ty >= 2.0f && ty < a.ly, yh[r] = ty >= 1.0f && ty < a.cmy;
+      xl[r] = tx >= 2.0f && tx < a.lx, xh[r] = tx >= 1.0f && tx < a.cmx;
+      off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kgen), wrap_mul(__float_as_int(ry), sH)),
+                     __float_as_int(rx));
+    } else {
+      const float rz = __fadd_rd(c[r][0], 8388608.0f), ry = __fadd_rd(c[r][1], 8388608.0f), rx = __fadd_rd(c[r][2], 8388608.0f);
+      f[r][0] = __fsub_rn(c[r][0], __fsub_rn(rz, 8388608.0f));
+      f[r][1] = __fsub_rn(c[r][1], __fsub_rn(ry, 8388608.0f));
+      f[r][2] = __fsub_rn(c[r][2], __fsub_rn(rx, 8388608.0f));
+      zl[r] = zh[r] = yl[r] = yh[r] = xl[r] = xh[r] = true;
+      off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kstrict), wrap_mul(__float_as_int(ry), sH)),
+                     __float_as_int(rx));
+    }
+    p0[r] = vb + off;  // corner 0; garbage when that corner is outside (never dereferenced then)
+  }
+  float v[NR][8];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const bool in = !GENERAL || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
+      v[r][k] = in ? __ldg(p0[r] + (k & 1) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0)) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    const float fz = f[r][0], fy = f[r][1], fx = f[r][2];
+    // seven lerps: x on the four rows, y on the two planes, z
+    const float dx0 = v[r][1] - v[r][0], dx1 = v[r][3] - v[r][2], dx2 = v[r][5] - v[r][4], dx3 = v[r][7] - v[r][6];
+    const float e0v = fmaf(fx, dx0, v[r][0]), e1 = fmaf(fx, dx1, v[r][2]), e2 = fmaf(fx, dx2, v[r][4]), e3 = fmaf(fx, dx3, v[r][6]);
+    const float dy0 = e1 - e0v, dy1 = e3 - e2;
+    const float g0 = fmaf(fy, dy0, e0v), g1 = fmaf(fy, dy1, e2);
+    const float dzv = g1 - g0;
+    const long long e = e0 + (long long)r * a.oW;
+    if constexpr (MODE == 0) {
+      if (valid) st_stream_f1(a.out + e, fmaf(fz, dzv, g0));
+    } else {
+      float go;
+      if constexpr (MODE == 2) {
+        const float o = fmaf(fz, dzv, g0);
+        const float x = o - tg[r];
+        // THNN SmoothL1Criterion: z = |x|; loss += z < 1 ? 0.5 z^2 : z - 0.5; gradient norm * clamp(x, -1, 1)
+        go = a.loss_norm * fminf(fmaxf(x, -1.0f), 1.0f);
+        if (valid) {
+          const float zz = fabsf(x);
+          L.lsum += zz < 1.0f ? 0.5f * zz * zz : zz - 0.5f;
+          const bool p = o > 0.5f, q = tg[r] > 0.5f;  // computeIOU (util.lua:110-120)
+          L.ni += (p && q) ? 1 : 0;
+          L.nu += (p || q) ? 1 : 0;
+          if (a.out) st_stream_f1(a.out + e, o);
+        }
+      } else {
+        go = tg[r];
+      }
+      if (!valid) go = 0.0f;
+      // d out / d coordinate (voxel units): z: dzv; y: lerp_z of the y differences; x: lerp_z lerp_y of the x differences
+      const float dyv = fmaf(fz, dy1 - dy0, dy0);
+      const float hx0 = fmaf(fy, dx1 - dx0, dx0), hx1 = fmaf(fy, dx3 - dx2, dx2);
+      const float dxv = fmaf(fz, hx1 - hx0, hx0);
+      const float gz = go * dzv, gy = go * dyv, gx = go * dxv;
+      L.S[0][0] = fmaf(wy[r].x, gz, L.S[0][0]), L.S[1][0] = fmaf(wy[r].y, gz, L.S[1][0]);
+      L.S[0][1] = fmaf(wy[r].x, gy, L.S[0][1]), L.S[1][1] = fmaf(wy[r].y, gy, L.S[1][1]);
+      L.S[0][2] = fmaf(wy[r].x, gx, L.S[0][2]), L.S[1][2] = fmaf(wy[r].y, gx, L.S[1][2]);
+      if constexpr (GV) {
+        // gradVol += corner weight * go (...c:737); gradVol has the volume's layout
+        const float ux = 1.0f - fx, uy = 1.0f - fy, uz = 1.0f - fz;
+        const float q[4] = {uz * uy * go, uz * fy * go, fz * uy * go, fz * fy * go};
+        float *g0p = const_cast<float *>(p0[r]) + a.gv_delta;
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const bool in = !GENERAL || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
+            if (in) red_add(g0p + (k & 1) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0), q[k >> 1] * ((k & 1) ? fx : ux));
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, bool GV, int VS, int NR>
+__device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__restrict__ vb, const float (&R)[2][3],
+                                           const float2 (&wy)[NR], long long e0, bool valid, BrickLane &L) {
+  float c[NR][3], tg[NR];
+  bool strict = true;
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    // coordinate in voxel units of the source: ((f + 1) * (size - 1)) / 2 = f * h + h with R = f-contributions * h
+    c[r][0] = fmaf(wy[r].x, R[0][0], fmaf(wy[r].y, R[1][0], a.hz2));
+    c[r][1] = fmaf(wy[r].x, R[0][1], fmaf(wy[r].y, R[1][1], a.hy2));
+    c[r][2] = fmaf(wy[r].x, R[0][2], fmaf(wy[r].y, R[1][2], a.hx2));
+    // 0 <= c < size - 1 on every axis: one unsigned compare per axis on the IEEE bits (negative and NaN patterns are larger)
+    strict = strict && (unsigned)__float_as_int(c[r][2]) < a.fbx && (unsigned)__float_as_int(c[r][1]) < a.fby &&
+             (unsigned)__float_as_int(c[r][0]) < a.fbz;
+    tg[r] = 0.0f;
+    if constexpr (MODE != 0) tg[r] = ld_stream_f1(a.tgt + e0 + (long long)r * a.oW);
+  }
+  if (__all_sync(0xffffffffu, strict))
+    brick_body<MODE, GV, VS, NR, false>(a, vb, c, wy, tg, e0, valid, L);
+  else
+    brick_body<MODE, GV, VS, NR, true>(a, vb, c, wy, tg, e0, valid, L);
+}
+
+#ifndef BRICK_MIN_CTAS
+#define BRICK_MIN_CTAS 3
+#endif
+#ifndef BRICK_NR
+#define BRICK_NR 2
+#endif
+
+template <int MODE, bool GV, int VS>
+__global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(const BrickArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BrickSmem m;
+  brick_fill(m, smem_raw, a);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  // task -> (z unit, z part, y unit, y part, x slot); consecutive warps take consecutive x slots, then y
+  int t = blockIdx.x * kBrickWarps + wid;
+  if (t >= a.ntask) return;
+  const int xs = t % a.nxs;
+  t /= a.nxs;
+  const int yp = t % a.ysplit;
+  t /= a.ysplit;
+  const int yu = t % a.nyu;
+  t /= a.nyu;
+  const int zp = t % a.zsplit, zu = t / a.zsplit;
+  int za = m.zs[zu], zb = m.zs[zu + 1], ya = m.ys[yu], yb = m.ys[yu + 1];
+  {
+    const int lz = zb - za, ly = yb - ya;
+    zb = za + (int)((long long)lz * (zp + 1) / a.zsplit), za += (int)((long long)lz * zp / a.zsplit);
+    yb = ya + (int)((long long)ly * (yp + 1) / a.ysplit), ya += (int)((long long)ly * yp / a.ysplit);
+  }
+  if (za >= zb || ya >= yb) return;
+
+  const int x = xs * 32 + lane;
+  const bool valid = x < a.oW;
+  const int xc = valid ? x : a.oW - 1;
+  const int kz0 = zu, kz1 = min(zu + 1, a.cD - 1), ky0 = yu, ky1 = min(yu + 1, a.cH - 1);
+  const long long plane = (long long)a.cD * a.cH * a.cW;
+  // per-lane state that is touched once per z lives in shared memory (registers are what limits the resident warps):
+  // sP[(j, k, c)]: the cage folded along x for this lane's column, corner (y: j, z: k) of the task's cell;
+  // sA[(j, k, c)]: its gradient
+  float *sP = m.lane + threadIdx.x, *sA = sP + 12 * kBrickThreads;
+  {
+    const int ix0 = m.ix[xc], ix1 = min(ix0 + 1, a.cW - 1);
+    const float2 wx = m.wx[xc];
+    const float *cb = a.cage + (long long)b * 3 * plane;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const long long o = ((long long)(k ? kz1 : kz0) * a.cH + (j ? ky1 : ky0)) * a.cW;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          sP[((j * 2 + k) * 3 + c) * kBrickThreads] = fmaf(wx.x, __ldg(cb + c * plane + o + ix0), wx.y * __ldg(cb + c * plane + o + ix1));
+          if constexpr (MODE != 0) sA[((j * 2 + k) * 3 + c) * kBrickThreads] = 0.0f;
+        }
+      }
+  }
+  const float hs[3] = {a.hz2, a.hy2, a.hx2};
+  BrickLane L;
+  L.lsum = 0.0f, L.ni = 0, L.nu = 0;
+
+  const float *vb = opaque(a.vol + (long long)b * a.vB);
+  const long long orow = (long long)a.oH * a.oW;
+  const long long eb = (long long)b * a.oD * orow + xc;  // element of (b, 0, 0, x) in out / gradOut / target
+
+  for (int z = za; z < zb; z++) {
+    const float2 wz = m.wz[z];
+    float R[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        R[j][c] = fmaf(wz.x, sP[((j * 2 + 0) * 3 + c) * kBrickThreads], wz.y * sP[((j * 2 + 1) * 3 + c) * kBrickThreads]) * hs[c];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) L.S[j][c] = 0.0f;
+    const long long ro = eb + (long long)z * orow;
+    int y = ya;
+    for (; y + BRICK_NR <= yb; y += BRICK_NR) {
+      float2 wy[BRICK_NR];
+#pragma unroll
+      for (int r = 0; r < BRICK_NR; r++) wy[r] = m.wy[y + r];
+      brick_rows<MODE, GV, VS, BRICK_NR>(a, vb, R, wy, ro + (long long)y * a.oW, valid, L);
+    }
+    for (; y < yb; y++) {
+      const float2 wy[1] = {m.wy[y]};
+      brick_rows<MODE, GV, VS, 1>(a, vb, R, wy, ro + (long long)y * a.oW, valid, L);
+    }
+    if constexpr (MODE != 0) {
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float *q = sA + ((j * 2) * 3 + c) * kBrickThreads;
+          q[0] = fmaf(wz.x, L.S[j][c], q[0]);
+          q[3 * kBrickThreads] = fmaf(wz.y, L.S[j][c], q[3 * kBrickThreads]);
+        }
+    }
+  }
+
+  if constexpr (MODE == 2) {
+    double ls = (double)L.lsum;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, d);
+    const int ni = __reduce_add_sync(0xffffffffu, L.ni), nu = __reduce_add_sync(0xffffffffu, L.nu);
+    if (lane == 0) {
+      atomicAdd(a.loss + b, ls);
+      if (a.iou) {
+        atomicAdd(a.iou + 2 * b, (unsigned long long)ni);
+        atomicAdd(a.iou + 2 * b + 1, (unsigned long long)nu);
+      }
+    }
+  }
+  if constexpr (MODE != 0) {
+    // the lanes of one cage column are consecutive: segmented reduction by doubling, heads add to the cage gradient
+    const int ix0 = m.ix[xc], ix1 = min(ix0 + 1, a.cW - 1);
+    const float2 wx = m.wx[xc];
+    bool same[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int ok = __shfl_down_sync(0xffffffffu, ix0, 1 << s);
+      same[s] = lane + (1 << s) < 32 && ok == ix0;
+    }
+    const int ix_prev = __shfl_up_sync(0xffffffffu, ix0, 1);  // every lane takes part (no short-circuit around a shuffle)
+    const bool head = lane == 0 || ix_prev != ix0;
+    float *gb = a.gcage + (long long)b * 3 * plane;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float g = sA[((j * 2 + k) * 3 + c) * kBrickThreads] * hs[c];
+          float lo = g * wx.x, hi = g * wx.y;
+#pragma unroll
+          for (int s = 0; s < 5; s++) {
+            const float l2 = __shfl_down_sync(0xffffffffu, lo, 1 << s), h2 = __shfl_down_sync(0xffffffffu, hi, 1 << s);
+            if (same[s]) lo += l2, hi += h2;
+          }
+          if (head) {
+            float *q = gb + c * plane + ((long long)(k ? kz1 : kz0) * a.cH + (j ? ky1 : ky0)) * a.cW;
+            if (lo != 0.0f) red_add(q + ix0, lo);
+            if (hi != 0.0f) red_add(q + ix1, hi);
+          }
+        }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool brick_supported(const BrickArgs &a) {
+  if (a.iD < 1 || a.iH < 1 || a.iW < 1 || a.iD > (1 << 22) || a.iH > (1 << 22) || a.iW > (1 << 22)) return false;
+  if ((long long)a.iD * a.iH * a.iW >= 0x7fffff00LL) return false;  // 32-bit in-sample offsets
+  if (a.oD < 2 || a.oH < 2 || a.oW < 2) return false;
+  if ((long long)a.oD * a.oH * a.oW >= 0x7fffff00LL) return false;
+  if (a.cD < 1 || a.cH < 1 || a.cW < 1) return false;
+  BrickArgs t = a;
+  return brick_smem_bytes(t) <= 160 * 1024;
+}
+
+// units, splits and the fast-tier constants; `B` decides how far the cells are split (about two waves of warps)
+void brick_plan(BrickArgs &a) {
+  a.nzu = brick_units(a.cD), a.nyu = brick_units(a.cH), a.nxs = (a.oW + 31) / 32;
+  a.zsplit = a.ysplit = 1;
+  const long long want = (long long)kSMs * BRICK_MIN_CTAS * kBrickWarps * 2;
+  double lz = (double)a.oD / a.nzu, ly = (double)a.oH / a.nyu;
+  long long tasks = (long long)a.B * a.nzu * a.nyu * a.nxs;
+  while (tasks < want && (lz / a.zsplit) * (ly / a.ysplit) >= 24.0) {
+    if (lz / a.zsplit >= ly / a.ysplit)
+      a.zsplit++;
+    else
+      a.ysplit++;
+    tasks = (long long)a.B * a.nzu * a.nyu * a.nxs * a.zsplit * a.ysplit;
+  }
+  if (const char *e = getenv("VOLSTN_BRICK_ZSPLIT")) {  // tuning only
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) a.zsplit = v;
+  }
+  if (const char *e = getenv("VOLSTN_BRICK_YSPLIT")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) a.ysplit = v;
+  }
+  a.ntask = a.nzu * a.zsplit * a.nyu * a.ysplit * a.nxs;
+  const float dm1 = (float)(a.iD - 1), hm1 = (float)(a.iH - 1), wm1 = (float)(a.iW - 1);
+  a.hz2 = dm1 * 0.5f, a.hy2 = hm1 * 0.5f, a.hx2 = wm1 * 0.5f;
+  memcpy(&a.fbz, &dm1, 4), memcpy(&a.fby, &hm1, 4), memcpy(&a.fbx, &wm1, 4);
+  a.cmz = (float)a.iD + 1.0f, a.cmy = (float)a.iH + 1.0f, a.cmx = (float)a.iW + 1.0f;
+  a.lz = (float)a.iD + 2.0f, a.ly = (float)a.iH + 2.0f, a.lx = (float)a.iW + 2.0f;
+  a.hz = a.cmz, a.hy = a.cmy, a.hx = a.cmx;
+  const unsigned sH = (unsigned)a.iW, sD = (unsigned)a.iH * sH;
+  a.kstrict = (int)(0u - 0x4B000000u * (sD + sH + 1u));
+  a.kgen = (int)(0u - 0x4B000002u * (sD + sH + 1u));
+}
+
+template <int MODE, bool GV, int VS>
+static int brick_launch_v(const BrickArgs &a, cudaStream_t st) {
+  const size_t smem = brick_smem_bytes(a);
+  if (smem > 48 * 1024)
+    VOLSTN_CUDA_TRY(cudaFuncSetAttribute(k_cage_brick<MODE, GV, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk = (a.ntask + kBrickWarps - 1) / kBrickWarps;
+  const long long cplane = 3LL * a.cD * a.cH * a.cW, oplane = (long long)a.oD * a.oH * a.oW;
+  for (int b0 = 0; b0 < a.B; b0 += 65535) {
+    BrickArgs c = a;
+    const int nb = a.B - b0 < 65535 ? a.B - b0 : 65535;
+    c.vol += (long long)b0 * a.vB;
+    c.cage += (long long)b0 * cplane;
+    if (c.gcage) c.gcage += (long long)b0 * cplane;
+    if (c.tgt) c.tgt += (long long)b0 * oplane;
+    if (c.out) c.out += (long long)b0 * oplane;
+    if (c.loss) c.loss += b0;
+    if (c.iou) c.iou += 2LL * b0;
+    k_cage_brick<MODE, GV, VS><<<dim3(nblk, nb), kBrickThreads, smem, st>>>(c);
+    int rc = after_launch();
+    if (rc) return rc;
+  }
+  return VOLSTN_OK;
+}
+
+template <int MODE, bool GV>
+static int brick_launch_t(const BrickArgs &a, cudaStream_t st) {
+  if (a.iW == a.iH && !getenv("VOLSTN_BRICK_NO_VS")) {
+    if (a.iW == 32) return brick_launch_v<MODE, GV, 32>(a, st);
+    if (a.iW == 64) return brick_launch_v<MODE, GV, 64>(a, st);
+    if (a.iW == 128) return brick_launch_v<MODE, GV, 128>(a, st);
+  }
+  return brick_launch_v<MODE, GV, 0>(a, st);
+}
+
+int brick_launch(const BrickArgs &a, int mode, bool grad_vol, cudaStream_t st) {
+  switch (mode) {
+    case 0: return brick_launch_t<0, false>(a, st);
+    case 1: return grad_vol ? brick_launch_t<1, true>(a, st) : brick_launch_t<1, false>(a, st);
+    default: return grad_vol ? brick_launch_t<2, true>(a, st) : brick_launch_t<2, false>(a, st);
+  }
+}
+
+}  // namespace volstn

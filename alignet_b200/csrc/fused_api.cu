@@ -9,6 +9,7 @@
 //                                                   (models/alignet_2d.lua:136-147 lifted to 3-D)
 #include <cstring>
 
+#include "cagebrick.cuh"
 #include "rowwarp.cuh"
 #include "volstn_internal.h"
 
@@ -160,6 +161,40 @@ int zero_grad_vol(const volstn_tensor5 *gradVol, cudaStream_t st) {
   return VOLSTN_OK;
 }
 
+
+// VOLSTN_FAST_ARITH on contiguous single-channel tensors: the brick kernels (cagebrick.cu).  Returns false when they do
+// not apply (the row kernels take the call).  `outlike`: out (forward), gradOut (backward) or the target (step).
+bool brick_args(BrickArgs &k, unsigned flags, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
+                const volstn_tensor5 *outlike, const volstn_tensor5 *gradVol) {
+  if (!(flags & VOLSTN_FAST_ARITH) || (flags & VOLSTN_ALGO_MASK) == VOLSTN_ALGO_ROW) return false;
+  if (flags & (VOLSTN_DEBUG_NO_FAST | VOLSTN_DEBUG_NO_BORDER)) return false;
+  if (vol->size[4] != 1 || !vol->data || !outlike->data) return false;
+  volstn_tensor5 v1 = *vol, o1 = *outlike;  // contiguous inside a sample; the batch stride is free
+  v1.size[0] = o1.size[0] = 1;
+  if (!desc_contiguous(&v1) || !desc_contiguous(&o1)) return false;
+  if (outlike->size[0] > 1 && outlike->stride[0] != outlike->size[1] * outlike->size[2] * outlike->size[3]) return false;
+  if (vol->stride[0] < 0) return false;
+  memset(&k, 0, sizeof(k));
+  for (int i = 1; i < 4; i++)
+    if (vol->size[i] > (1 << 22) || outlike->size[i] > (1 << 22)) return false;
+  k.vol = static_cast<const float *>(vol->data);
+  k.cage = static_cast<const float *>(cage);
+  k.vB = vol->stride[0];
+  k.B = (int)vol->size[0];
+  k.iD = (int)vol->size[1], k.iH = (int)vol->size[2], k.iW = (int)vol->size[3];
+  k.oD = (int)outlike->size[1], k.oH = (int)outlike->size[2], k.oW = (int)outlike->size[3];
+  k.cD = (int)cage_dims[0], k.cH = (int)cage_dims[1], k.cW = (int)cage_dims[2];
+  if (gradVol) {
+    if (!gradVol->data) return false;
+    for (int i = 0; i < 5; i++)
+      if (gradVol->size[i] != vol->size[i] || (vol->size[i] > 1 && gradVol->stride[i] != vol->stride[i])) return false;
+    k.gv_delta = static_cast<const float *>(gradVol->data) - k.vol;
+  }
+  if (!brick_supported(k)) return false;
+  brick_plan(k);
+  return true;
+}
+
 }  // namespace
 }  // namespace volstn
 
@@ -264,6 +299,13 @@ int volstn_b200_cage_warp_forward(int dtype, const void *cage, const int64_t cag
   if (out->size[1] < 2 || out->size[2] < 2 || out->size[3] < 2) return VOLSTN_ERR_SHAPE;
   if (desc_numel(out) == 0) return VOLSTN_OK;
   if (!cage) return VOLSTN_ERR_ARG;
+  {
+    BrickArgs k;
+    if (brick_args(k, flags, cage, cage_dims, vol, out, nullptr)) {
+      k.out = static_cast<float *>(out->data);
+      return brick_launch(k, 0, false, static_cast<cudaStream_t>(cuda_stream));
+    }
+  }
   RowArgs a;
   RowPlan p;
   zero_args(a);
@@ -303,6 +345,14 @@ int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t ca
   }
   if (desc_numel(gradOut) == 0) return VOLSTN_OK;
   if (!cage) return VOLSTN_ERR_ARG;
+  if (!ov) {
+    BrickArgs k;
+    if (brick_args(k, flags, cage, cage_dims, vol, gradOut, og ? nullptr : gradVol)) {
+      k.tgt = static_cast<const float *>(gradOut->data);
+      k.gcage = static_cast<float *>(gradCage);
+      return brick_launch(k, 1, !og, st);
+    }
+  }
   RowArgs a;
   RowPlan p;
   zero_args(a);
@@ -354,6 +404,18 @@ int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_d
   if (iou_counts) VOLSTN_CUDA_TRY(cudaMemsetAsync(iou_counts, 0, (size_t)B * 2 * sizeof(uint64_t), st));
   if (desc_numel(target) == 0) return VOLSTN_OK;
   if (!cage || (out && !out->data)) return VOLSTN_ERR_ARG;
+  {
+    BrickArgs k;
+    if (brick_args(k, flags, cage, cage_dims, vol, target, og ? nullptr : gradVol)) {
+      k.tgt = static_cast<const float *>(target->data);
+      k.out = out ? static_cast<float *>(out->data) : nullptr;
+      k.gcage = static_cast<float *>(gradCage);
+      k.loss_norm = grad_scale;
+      k.loss = loss_sum;
+      k.iou = reinterpret_cast<unsigned long long *>(iou_counts);
+      return brick_launch(k, 2, !og, st);
+    }
+  }
   RowArgs a;
   RowPlan p;
   zero_args(a);

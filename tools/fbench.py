@@ -90,6 +90,20 @@ def main():
         report("affine FUSED bwd (gradVol + gradT)", b_fus, 12 * V, f"x{(b_s + b_gen) / b_fus:.2f}")
         del grid, gg
 
+    if "cagefast" in what:
+        # the VOLSTN_FAST_ARITH lines only (brick kernels): quick A/B of library variants
+        cage = torch.from_numpy(synth.alignet_cage(nb, csz, rng).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
+        fast, fast_full = vnn.CageWarpVolumetric(onlyGrid=True, fastArith=True), vnn.CageWarpVolumetric(fastArith=True)
+        tgt = rep(synth.volume("v2", nb, N, N, N, 1, rng))
+        report("cage FUSED fwd, fast arithmetic", timed(lambda: fast.updateOutput([vol, cage])), 8 * V)
+        report("cage FUSED bwd (gradCage only), fast arithmetic", timed(lambda: fast.updateGradInput([vol, cage], go)), 8 * V)
+        report("cage FUSED bwd (gradSource + gradCage), fast arithmetic", timed(lambda: fast_full.updateGradInput([vol, cage], go)), 12 * V)
+        stp = vnn.CageWarpSmoothL1Volumetric(fastArith=True)
+        report("cage STEP (fwd + SmoothL1 + IoU + bwd to the cage), fast arithmetic", timed(lambda: stp.forwardBackward([vol, cage], tgt)), 8 * V)
+        idc = torch.from_numpy(synth.alignet_cage(nb, csz, rng, jitter=0.0).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
+        if True:
+            report("cage STEP, fast arithmetic, IDENTITY cage", timed(lambda: stp.forwardBackward([vol, idc], tgt)), 8 * V)
+
     if "cage" in what:
         cage = torch.from_numpy(synth.alignet_cage(nb, csz, rng).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
         cage_vol = torch.ones((B, csz, csz, csz, 4), device="cuda"); cage_vol[..., :3] = cage.permute(0, 2, 3, 4, 1)
