@@ -30,99 +30,23 @@
 
 namespace volstn {
 
-constexpr int kBrickThreads = 256;
-constexpr int kBrickWarps = kBrickThreads / 32;
-
-// (float)(-1 + k/(n-1)*2) in double: VolumetricGridGenerator.lua:17-19 (as rowwarp.cu::row_base_coord)
-__device__ __forceinline__ float brick_base_coord(int k, int n) {
-  return (float)(-1.0 + (double)k / (double)(n - 1) * 2.0);
-}
-
-struct BrickSmem {
-  float2 *wz, *wy, *wx;  // (weight of the low cage corner, weight of the high one) per output position
-  int *iz, *iy, *ix;     // low cage corner per output position, remapped so that the high corner exists (see brick_fill)
-  int *zs, *ys;          // first position of z / y unit k (k = 0 .. units)
-  float *lane;           // per-thread slots: 12 folded cage values, 12 gradient accumulators ([slot][thread])
-};
-
-__host__ __device__ inline int brick_units(int cn) { return cn > 1 ? cn - 1 : 1; }
-
-__host__ __device__ inline size_t brick_smem_bytes(const BrickArgs &a) {
-  const size_t axes = (size_t)a.oD + a.oH + a.oW;
-  return 24 * 256 * 4 + axes * 12 + (size_t)(brick_units(a.cD) + brick_units(a.cH) + 2) * 4 + 16;
-}
-
-__device__ __forceinline__ void brick_fill(BrickSmem &m, unsigned char *raw, const BrickArgs &a) {
-  const int oD = a.oD, oH = a.oH, oW = a.oW, axes = oD + oH + oW;
-  m.lane = reinterpret_cast<float *>(raw);
-  m.wz = reinterpret_cast<float2 *>(raw + 24 * 256 * 4);
-  m.wy = m.wz + oD;
-  m.wx = m.wy + oH;
-  m.iz = reinterpret_cast<int *>(m.wz + axes);
-  m.iy = m.iz + oD;
-  m.ix = m.iy + oH;
-  m.zs = m.iz + axes;
-  m.ys = m.zs + brick_units(a.cD) + 1;
-  // the sampler's own set-up (...c:507-517) of the identity coordinate of every axis position.  The identity coordinate
-  // never leaves [0, cn - 1]; its last position sits ON the last cage node (i0 = cn - 1, low weight 1, high corner in
-  // the zero padding): there the cell below with weights (0, 1) is the same value, and every position of an axis then
-  // has its high corner inside the cage.  A one-node axis keeps (i0 = 0, high weight 0).
-  for (int i = threadIdx.x; i < axes; i += blockDim.x) {
-    int k, n, cn;
-    if (i < oD)
-      k = i, n = oD, cn = a.cD;
-    else if (i < oD + oH)
-      k = i - oD, n = oH, cn = a.cH;
-    else
-      k = i - oD - oH, n = oW, cn = a.cW;
-    int i0;
-    float w;
-    axis_setup<float>(brick_base_coord(k, n), (float)(cn - 1), i0, w);
-    float2 ww = make_float2(w, 1.0f - w);
-    if (cn == 1)
-      i0 = 0, ww = make_float2(w, 0.0f);
-    else if (i0 >= cn - 1)
-      i0 = cn - 2, ww = make_float2(1.0f - w, w);  // w == 1 there: weights (0, 1) on the cell below
-    else if (i0 < 0)
-      i0 = 0, ww = make_float2(1.0f, 0.0f);        // cannot happen (the coordinate is >= 0); keeps the indices safe
-    m.wz[i] = ww;  // wz / wy / wx and iz / iy / ix are consecutive
-    m.iz[i] = i0;
-  }
-  __syncthreads();
-  // unit k of an axis = the positions whose (remapped) low corner is k: a contiguous, possibly empty range
-  const int nzu = brick_units(a.cD), nyu = brick_units(a.cH);
-  for (int i = threadIdx.x; i <= nzu + nyu + 1; i += blockDim.x) {
-    const bool isz = i <= nzu;
-    const int k = isz ? i : i - nzu - 1, n = isz ? oD : oH, units = isz ? nzu : nyu;
-    const int *tab = isz ? m.iz : m.iy;
-    int first = n;
-    if (k < units) {
-      first = 0;
-      while (first < n && tab[first] < k) first++;
-    }
-    (isz ? m.zs : m.ys)[k] = first;
-  }
-  __syncthreads();
-}
-
 // ---------------------------------------------------------------------------------------------
 // NR consecutive rows of the task: coordinates -> ONE tier vote -> all gathers in flight -> values, derivatives, sinks
 // ---------------------------------------------------------------------------------------------
 struct BrickLane {
-  float S[2][3];  // gradient of R[j][c], accumulated over the rows of one z
-  float lsum;     // SmoothL1 terms of this lane (float: at most a few thousand terms of O(1) per task)
-  int ni, nu;     // IoU counts of this lane
+  float T0[3], T1[3];  // sums over the rows of one z of g_c and of wy_hi . g_c (g = gradient of the voxel's coordinates)
+  float lsum;          // SmoothL1 terms of this lane (float: at most a few thousand terms of O(1) per task)
+  int ni, nu;          // IoU counts of this lane
 };
 
 // MODE: 0 = forward (store out), 1 = backward from gradOut, 2 = training step (SmoothL1 + IoU + backward, optional out)
 // VS: 0 = run-time strides of the source volume, else iW = iH = VS (row and plane offsets are immediates of the loads)
-// The kernels are LATENCY-bound, not issue-bound (first version, one vote and one row at a time: 145 us forward at
-// 64^3 x 64 with ~70 instructions per voxel-warp): the rows of a trip share one vote so that all their gathers are in
-// flight together, and the target / gradOut element of every row is requested before the vote.
+// The rows of a trip share one tier vote so that all their gathers are in flight together, and the target / gradOut
+// element of every row is requested before the vote.
 template <int MODE, bool GV, int VS, int NR, bool GENERAL>
 __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__restrict__ vb, const float (&c)[NR][3],
-                                           const float2 (&wy)[NR], const float (&tg)[NR], long long e0, bool valid,
-                                           BrickLane &L) {
+                                           const float (&wyh)[NR], const float (&tg)[NR], const float *__restrict__ tp,
+                                           float *__restrict__ op, bool valid, BrickLane &L) {
   const int sH = VS ? VS : a.iW, sD = VS ? VS * VS : a.iH * a.iW;
   float f[NR][3];
   const float *p0[NR];
@@ -146,10 +70,15 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
       off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kgen), wrap_mul(__float_as_int(ry), sH)),
                      __float_as_int(rx));
     } else {
-      const float rz = __fadd_rd(c[r][0], 8388608.0f), ry = __fadd_rd(c[r][1], 8388608.0f), rx = __fadd_rd(c[r][2], 8388608.0f);
-      f[r][0] = __fsub_rn(c[r][0], __fsub_rn(rz, 8388608.0f));
-      f[r][1] = __fsub_rn(c[r][1], __fsub_rn(ry, 8388608.0f));
-      f[r][2] = __fsub_rn(c[r][2], __fsub_rn(rx, 8388608.0f));
+      // -eps <= c < size - 1 on every axis.  A coordinate that rounding left a hair below 0 (the identity cage puts a
+      // whole face there) is read as 0: the value moves by less than eps x slope.  The HIGH face stays with the general
+      // tier: ON it the reference takes the cell outside (high corners in the zero padding, ...c:542-564), and the
+      // identity cage puts a whole face exactly there.
+      const float cz = fmaxf(c[r][0], 0.0f), cy = fmaxf(c[r][1], 0.0f), cx = fmaxf(c[r][2], 0.0f);
+      const float rz = __fadd_rd(cz, 8388608.0f), ry = __fadd_rd(cy, 8388608.0f), rx = __fadd_rd(cx, 8388608.0f);
+      f[r][0] = __fsub_rn(cz, __fsub_rn(rz, 8388608.0f));
+      f[r][1] = __fsub_rn(cy, __fsub_rn(ry, 8388608.0f));
+      f[r][2] = __fsub_rn(cx, __fsub_rn(rx, 8388608.0f));
       zl[r] = zh[r] = yl[r] = yh[r] = xl[r] = xh[r] = true;
       off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kstrict), wrap_mul(__float_as_int(ry), sH)),
                      __float_as_int(rx));
@@ -174,9 +103,8 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
     const float dy0 = e1 - e0v, dy1 = e3 - e2;
     const float g0 = fmaf(fy, dy0, e0v), g1 = fmaf(fy, dy1, e2);
     const float dzv = g1 - g0;
-    const long long e = e0 + (long long)r * a.oW;
     if constexpr (MODE == 0) {
-      if (valid) st_stream_f1(a.out + e, fmaf(fz, dzv, g0));
+      if (valid) st_stream_f1(op + r * a.oW, fmaf(fz, dzv, g0));
     } else {
       float go;
       if constexpr (MODE == 2) {
@@ -188,9 +116,9 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
           const float zz = fabsf(x);
           L.lsum += zz < 1.0f ? 0.5f * zz * zz : zz - 0.5f;
           const bool p = o > 0.5f, q = tg[r] > 0.5f;  // computeIOU (util.lua:110-120)
-          L.ni += (p && q) ? 1 : 0;
-          L.nu += (p || q) ? 1 : 0;
-          if (a.out) st_stream_f1(a.out + e, o);
+          L.ni += (p & q) ? 1 : 0;
+          L.nu += (p | q) ? 1 : 0;
+          if (op) st_stream_f1(op + r * a.oW, o);
         }
       } else {
         go = tg[r];
@@ -201,9 +129,9 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
       const float hx0 = fmaf(fy, dx1 - dx0, dx0), hx1 = fmaf(fy, dx3 - dx2, dx2);
       const float dxv = fmaf(fz, hx1 - hx0, hx0);
       const float gz = go * dzv, gy = go * dyv, gx = go * dxv;
-      L.S[0][0] = fmaf(wy[r].x, gz, L.S[0][0]), L.S[1][0] = fmaf(wy[r].y, gz, L.S[1][0]);
-      L.S[0][1] = fmaf(wy[r].x, gy, L.S[0][1]), L.S[1][1] = fmaf(wy[r].y, gy, L.S[1][1]);
-      L.S[0][2] = fmaf(wy[r].x, gx, L.S[0][2]), L.S[1][2] = fmaf(wy[r].y, gx, L.S[1][2]);
+      L.T0[0] += gz, L.T1[0] = fmaf(wyh[r], gz, L.T1[0]);
+      L.T0[1] += gy, L.T1[1] = fmaf(wyh[r], gy, L.T1[1]);
+      L.T0[2] += gx, L.T1[2] = fmaf(wyh[r], gx, L.T1[2]);
       if constexpr (GV) {
         // gradVol += corner weight * go (...c:737); gradVol has the volume's layout
         const float ux = 1.0f - fx, uy = 1.0f - fy, uz = 1.0f - fz;
@@ -221,27 +149,28 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
   }
 }
 
+// C0[c]: the voxel coordinate (source voxel units) at the low y corner of the row's cage cell, D[c] = high - low
 template <int MODE, bool GV, int VS, int NR>
-__device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__restrict__ vb, const float (&R)[2][3],
-                                           const float2 (&wy)[NR], long long e0, bool valid, BrickLane &L) {
+__device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__restrict__ vb, const float (&C0)[3],
+                                           const float (&D)[3], const float (&wyh)[NR], const float *__restrict__ tp,
+                                           float *__restrict__ op, bool valid, BrickLane &L) {
   float c[NR][3], tg[NR];
   bool strict = true;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    // coordinate in voxel units of the source: ((f + 1) * (size - 1)) / 2 = f * h + h with R = f-contributions * h
-    c[r][0] = fmaf(wy[r].x, R[0][0], fmaf(wy[r].y, R[1][0], a.hz2));
-    c[r][1] = fmaf(wy[r].x, R[0][1], fmaf(wy[r].y, R[1][1], a.hy2));
-    c[r][2] = fmaf(wy[r].x, R[0][2], fmaf(wy[r].y, R[1][2], a.hx2));
-    // 0 <= c < size - 1 on every axis: one unsigned compare per axis on the IEEE bits (negative and NaN patterns are larger)
-    strict = strict && (unsigned)__float_as_int(c[r][2]) < a.fbx && (unsigned)__float_as_int(c[r][1]) < a.fby &&
-             (unsigned)__float_as_int(c[r][0]) < a.fbz;
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[r][i] = fmaf(wyh[r], D[i], C0[i]);
+    // -eps <= c < size - 1 on every axis: one unsigned compare per axis on the IEEE bits of c + eps (negative and NaN
+    // patterns are larger than any positive bound)
+    strict = strict & ((unsigned)__float_as_int(c[r][0] + a.ez) < a.ubz) & ((unsigned)__float_as_int(c[r][1] + a.ey) < a.uby) &
+             ((unsigned)__float_as_int(c[r][2] + a.ex) < a.ubx);
     tg[r] = 0.0f;
-    if constexpr (MODE != 0) tg[r] = ld_stream_f1(a.tgt + e0 + (long long)r * a.oW);
+    if constexpr (MODE != 0) tg[r] = ld_stream_f1(tp + r * a.oW);
   }
   if (__all_sync(0xffffffffu, strict))
-    brick_body<MODE, GV, VS, NR, false>(a, vb, c, wy, tg, e0, valid, L);
+    brick_body<MODE, GV, VS, NR, false>(a, vb, c, wyh, tg, tp, op, valid, L);
   else
-    brick_body<MODE, GV, VS, NR, true>(a, vb, c, wy, tg, e0, valid, L);
+    brick_body<MODE, GV, VS, NR, true>(a, vb, c, wyh, tg, tp, op, valid, L);
 }
 
 #ifndef BRICK_MIN_CTAS
@@ -287,7 +216,7 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
   float *sP = m.lane + threadIdx.x, *sA = sP + 12 * kBrickThreads;
   {
     const int ix0 = m.ix[xc], ix1 = min(ix0 + 1, a.cW - 1);
-    const float2 wx = m.wx[xc];
+    const float wxh = m.wx[xc].y;
     const float *cb = a.cage + (long long)b * 3 * plane;
 #pragma unroll
     for (int j = 0; j < 2; j++)
@@ -296,7 +225,9 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
         const long long o = ((long long)(k ? kz1 : kz0) * a.cH + (j ? ky1 : ky0)) * a.cW;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          sP[((j * 2 + k) * 3 + c) * kBrickThreads] = fmaf(wx.x, __ldg(cb + c * plane + o + ix0), wx.y * __ldg(cb + c * plane + o + ix1));
+          // low + w_hi . (high - low): exactly `low` where the two nodes coincide (e.g. the identity cage's own axis)
+          const float lo = __ldg(cb + c * plane + o + ix0), hi = __ldg(cb + c * plane + o + ix1);
+          sP[((j * 2 + k) * 3 + c) * kBrickThreads] = fmaf(wxh, hi - lo, lo);
           if constexpr (MODE != 0) sA[((j * 2 + k) * 3 + c) * kBrickThreads] = 0.0f;
         }
       }
@@ -306,42 +237,45 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
   L.lsum = 0.0f, L.ni = 0, L.nu = 0;
 
   const float *vb = opaque(a.vol + (long long)b * a.vB);
-  const long long orow = (long long)a.oH * a.oW;
-  const long long eb = (long long)b * a.oD * orow + xc;  // element of (b, 0, 0, x) in out / gradOut / target
+  const long long osample = (long long)a.oD * a.oH * a.oW;  // < 2^31: in-sample element offsets are 32-bit
+  const float *tb = (MODE != 0) ? opaque(a.tgt + (long long)b * osample + xc) : nullptr;
+  float *ob = a.out ? opaque(a.out + (long long)b * osample + xc) : nullptr;
 
   for (int z = za; z < zb; z++) {
     const float2 wz = m.wz[z];
-    float R[2][3];
+    float C0[3], D[3];
 #pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        R[j][c] = fmaf(wz.x, sP[((j * 2 + 0) * 3 + c) * kBrickThreads], wz.y * sP[((j * 2 + 1) * 3 + c) * kBrickThreads]) * hs[c];
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int c = 0; c < 3; c++) L.S[j][c] = 0.0f;
-    const long long ro = eb + (long long)z * orow;
-    int y = ya;
-    for (; y + BRICK_NR <= yb; y += BRICK_NR) {
-      float2 wy[BRICK_NR];
-#pragma unroll
-      for (int r = 0; r < BRICK_NR; r++) wy[r] = m.wy[y + r];
-      brick_rows<MODE, GV, VS, BRICK_NR>(a, vb, R, wy, ro + (long long)y * a.oW, valid, L);
+    for (int c = 0; c < 3; c++) {
+      // the normalised field at the two y corners, then ((f + 1) * (size - 1)) / 2 = f * h + h: source voxel units
+      const float p00 = sP[((0 * 2 + 0) * 3 + c) * kBrickThreads], p01 = sP[((0 * 2 + 1) * 3 + c) * kBrickThreads];
+      const float p10 = sP[((1 * 2 + 0) * 3 + c) * kBrickThreads], p11 = sP[((1 * 2 + 1) * 3 + c) * kBrickThreads];
+      const float c0 = fmaf(fmaf(wz.y, p01 - p00, p00), hs[c], hs[c]), c1 = fmaf(fmaf(wz.y, p11 - p10, p10), hs[c], hs[c]);
+      C0[c] = c0, D[c] = c1 - c0;
+      L.T0[c] = L.T1[c] = 0.0f;
     }
-    for (; y < yb; y++) {
-      const float2 wy[1] = {m.wy[y]};
-      brick_rows<MODE, GV, VS, 1>(a, vb, R, wy, ro + (long long)y * a.oW, valid, L);
+    unsigned eo = (unsigned)(z * a.oH + ya) * (unsigned)a.oW;
+    int y = ya;
+    for (; y + BRICK_NR <= yb; y += BRICK_NR, eo += BRICK_NR * a.oW) {
+      float wyh[BRICK_NR];
+#pragma unroll
+      for (int r = 0; r < BRICK_NR; r++) wyh[r] = m.wy[y + r].y;
+      brick_rows<MODE, GV, VS, BRICK_NR>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
+    }
+    for (; y < yb; y++, eo += a.oW) {
+      const float wyh[1] = {m.wy[y].y};
+      brick_rows<MODE, GV, VS, 1>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
     }
     if constexpr (MODE != 0) {
+      // c = C0 + wy_hi (C1 - C0): d/dC1 = T1, d/dC0 = T0 - T1; C_j = F_j h + h and F_j = P_j0 + wz_hi (P_j1 - P_j0)
 #pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          float *q = sA + ((j * 2) * 3 + c) * kBrickThreads;
-          q[0] = fmaf(wz.x, L.S[j][c], q[0]);
-          q[3 * kBrickThreads] = fmaf(wz.y, L.S[j][c], q[3 * kBrickThreads]);
-        }
+      for (int c = 0; c < 3; c++) {
+        const float d1 = L.T1[c], d0 = L.T0[c] - d1;
+        float *q = sA + c * kBrickThreads;
+        q[0] = fmaf(wz.x, d0, q[0]);
+        q[3 * kBrickThreads] = fmaf(wz.y, d0, q[3 * kBrickThreads]);
+        q[6 * kBrickThreads] = fmaf(wz.x, d1, q[6 * kBrickThreads]);
+        q[9 * kBrickThreads] = fmaf(wz.y, d1, q[9 * kBrickThreads]);
+      }
     }
   }
 
@@ -438,6 +372,19 @@ void brick_plan(BrickArgs &a) {
   const unsigned sH = (unsigned)a.iW, sD = (unsigned)a.iH * sH;
   a.kstrict = (int)(0u - 0x4B000000u * (sD + sH + 1u));
   a.kgen = (int)(0u - 0x4B000002u * (sD + sH + 1u));
+  // strict tier: -eps <= c < size - 1 with eps = size * 2^-23 (a few ulp of the coordinate), tested as
+  // bits(c + eps) < bits(size - 1 + eps): rounding is monotone, so c = size - 1 itself never passes
+  {
+    const int sz[3] = {a.iD, a.iH, a.iW};
+    float *eps[3] = {&a.ez, &a.ey, &a.ex};
+    unsigned *ub[3] = {&a.ubz, &a.uby, &a.ubx};
+    for (int i = 0; i < 3; i++) {
+      const float e = (float)sz[i] * 1.1920929e-7f, hi = (float)(sz[i] - 1) + e;
+      *eps[i] = e;
+      *ub[i] = 0;  // a one-voxel axis has no cell: always the general tier
+      if (sz[i] > 1) memcpy(ub[i], &hi, 4);
+    }
+  }
 }
 
 template <int MODE, bool GV, int VS>

@@ -49,7 +49,7 @@ struct RowSmem {
   float *gc;     // CAGE backward: gradient of the cage, same cells x 3
   int *xs;       // CAGE backward: xs[t] = first x whose low cage cell is >= t  (t = 0 .. cW)
   float *stage;  // CAGE backward: per warp, per slot: 6 x oWp products (wx * gg[c], (1 - wx) * gg[c])
-  float *nodes;  // CAGE, fast arithmetic: per warp, per row of the trip: cW + 2 (z, y) pairs, then cW + 2 x values (cage_nodes)
+  float *nodes;  // CAGE, fast arithmetic: per warp, per row of the trip: nstride (z, y) pairs, then nstride x values (cage_nodes)
   int4 *nitem;   // CAGE, fast arithmetic: the (node, component) item lane `i` (and i + 32) computes for every row
 };
 
@@ -57,13 +57,16 @@ __host__ __device__ inline int row_cells(const RowArgs &a) { return (a.cD + 1) *
 // staging row length: a multiple of 32 plus 8, so that the three channels of a cage cell (rows c and 3 + c of the
 // stage) fall into different shared-memory banks when the item lanes sum their segments
 __host__ __device__ inline int row_owp(const RowArgs &a) { return ((a.s.oW + 31) & ~31) + 8; }
+// fast arithmetic: floats per component of a row's node vector, EVEN so that the (z, y) pairs of the second row of a trip
+// (3 * nstride floats further) stay 8-byte aligned (an odd cage width faulted with `misaligned address`)
+__host__ __device__ inline int row_nstride(const RowArgs &a) { return (a.cW + 3) & ~1; }
 
 template <int SRC, bool BWD>
 __host__ __device__ inline size_t row_smem_bytes(const RowArgs &a, bool two_rows) {
   const size_t axes = (size_t)a.s.oD + a.s.oH + a.s.oW;
   if (SRC == ROW_SRC_AFFINE) return axes * 4;
   if (SRC == ROW_SRC_CAGE) {
-    size_t n = (size_t)row_cells(a) * 16 + axes * 8 + 8 + 64 * 16 + (size_t)kRowWarps * 2 * (a.cW + 2) * 12;
+    size_t n = (size_t)row_cells(a) * 16 + axes * 8 + 8 + 64 * 16 + (size_t)kRowWarps * 2 * row_nstride(a) * 12;
     if (BWD) n += (size_t)row_cells(a) * 12 + (size_t)(a.cW + 2) * 4 + (size_t)kRowWarps * (two_rows ? 2 : 1) * 6 * row_owp(a) * 4;
     return n;
   }
@@ -90,7 +93,7 @@ __device__ __forceinline__ void row_carve(RowSmem &m, unsigned char *raw, const 
     m.nitem = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(m.ix + oW) + ((oD + oH + oW) & 1) * 8);  // 16-byte aligned
     m.nodes = reinterpret_cast<float *>(m.nitem + 64);
     if constexpr (BWD) {
-      m.gc = m.nodes + kRowWarps * 2 * 3 * (a.cW + 2);
+      m.gc = m.nodes + kRowWarps * 2 * 3 * row_nstride(a);
       m.xs = reinterpret_cast<int *>(m.gc + 3 * row_cells(a));
       m.stage = reinterpret_cast<float *>(m.xs + a.cW + 2);
     }
@@ -151,7 +154,7 @@ __device__ __forceinline__ void row_fill(const RowSmem &m, const RowArgs &a, int
       const int cWp = a.cW + 1, it = threadIdx.x;
       const int c = it / cWp, t = it - c * cWp;
       int4 e = make_int4(-1, 0, 0, 0);
-      if (c < 3) e = c < 2 ? make_int4(t, c, 2, 2 * t + c) : make_int4(t, 2 * row_cells(a), 1, 2 * (a.cW + 2) + t);
+      if (c < 3) e = c < 2 ? make_int4(t, c, 2, 2 * t + c) : make_int4(t, 2 * row_cells(a), 1, 2 * row_nstride(a) + t);
       m.nitem[it] = e;
     }
     if constexpr (BWD) {
@@ -213,7 +216,7 @@ __device__ __forceinline__ void cage_field(const RowSmem &m, const RowArgs &a, i
 // (cW + 1 nodes x 3 components, one (node, component) item per lane) and, per VOXEL, two node loads and three lerps.
 // Same mathematics, different rounding: the field agrees with cage_field() to a few ulp (tests: <= 1e-6 absolute on
 // coordinates in [-1, 1]), NOT bit for bit -- hence a flag, off by default.
-// nodes of output row (z, y) into `nbuf` (one row's 3 * (cW + 2) floats of this warp's buffer)
+// nodes of output row (z, y) into `nbuf` (one row's 3 * nstride floats of this warp's buffer)
 __device__ __forceinline__ void cage_nodes(const RowSmem &m, const RowArgs &a, float *nbuf, int z, int y, int lane) {
   const int cWp = a.cW + 1, cHWp = (a.cH + 1) * cWp;
   const float wy = m.ty[y], wz = m.tz[z];
@@ -297,12 +300,12 @@ struct RowCoords {
   // per-CTA state of the source
   float t[12];
   const float *gb;
-  // fast arithmetic: this warp's node buffer (two rows of 3 * (cW + 2) floats)
+  // fast arithmetic: this warp's node buffer (two rows of 3 * nstride floats)
   float *nbuf;
   int nstride, nlane;
   __device__ __forceinline__ void init_nodes(const RowSmem &m, const RowArgs &a, int wid, int lane) {
     if constexpr (SRC == ROW_SRC_CAGE && FASTM) {
-      nstride = a.cW + 2;
+      nstride = row_nstride(a);
       nbuf = m.nodes + wid * 2 * 3 * nstride;
       nlane = lane;
     }

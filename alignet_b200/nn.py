@@ -579,17 +579,18 @@ class CageWarpVolumetric(Module):
     ``onlyGrid=True`` skips gradSource (the source is data behind nn.Identity, models/alignet_2d.lua:23-24)."""
 
     def __init__(self, depth: Optional[int] = None, height: Optional[int] = None, width: Optional[int] = None,
-                 layout: str = "BDHWC", onlyGrid: bool = False, fastArith: bool = False):
+                 layout: str = "BDHWC", onlyGrid: bool = False, fastArith: bool = False, algo: int = 0):
         super().__init__()
         assert layout in ("BDHWC", "BCDHW")
         self.depth, self.height, self.width, self.layout, self.onlyGrid = depth, height, width, layout, onlyGrid
+        self.algo = algo  # _abi.ALGO_ROW keeps the row kernels where the brick kernels would run (A/B timing and tests)
         # VOLSTN_FAST_ARITH (single-channel volumes): separable cage up-sample, FMA sums, factored gradGrid -- values within
         # 1e-5 of the reference chain instead of bit-identical (include/volstn_b200.h)
         self.fastArith = fastArith
         self.gradInput = []
 
     def _fast(self) -> int:
-        return _abi.FAST_ARITH if self.fastArith else 0
+        return (_abi.FAST_ARITH if self.fastArith else 0) | (self.algo & 0xF00)
 
     def _out_dims(self, v):
         return (self.depth or v.size(1), self.height or v.size(2), self.width or v.size(3))
@@ -665,9 +666,11 @@ class CageWarpSmoothL1Volumetric(Module):
     the exact ``B x 2`` (intersection, union) counts, ``self.output`` the warped volume if ``keepOutput``.
     Single-channel ``B x D x H x W x 1`` CUDA float volumes."""
 
-    def __init__(self, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False, fastArith: bool = False):
+    def __init__(self, sizeAverage: bool = True, onlyGrid: bool = True, keepOutput: bool = False, fastArith: bool = False,
+                 algo: int = 0):
         super().__init__()
         self.sizeAverage, self.onlyGrid, self.keepOutput, self.fastArith = sizeAverage, onlyGrid, keepOutput, fastArith
+        self.algo = algo  # _abi.ALGO_ROW: the row kernels (A/B timing and tests)
         self.gradInput = []
         self.loss = self.lossPerSample = self.iouCounts = None
 
@@ -690,7 +693,7 @@ class CageWarpSmoothL1Volumetric(Module):
         # THNN: norm = sizeAverage ? 1. / ((real)nElement) : 1.  (double division, stored in `real`)
         norm = float(torch.tensor(1.0 / float(torch.tensor(float(n), dtype=torch.float32)), dtype=torch.float32)) if self.sizeAverage else 1.0
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
-        flags = _abi.BWD_ZERO_GRADVOL | (_abi.FAST_ARITH if self.fastArith else 0)
+        flags = _abi.BWD_ZERO_GRADVOL | (_abi.FAST_ARITH if self.fastArith else 0) | (self.algo & 0xF00)
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
             gv.zero_()

@@ -783,6 +783,18 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         "fused_modules_plus_elementwise_criterion_ms": c_s, "one_kernel_ms": f_s, "speedup": c_s / f_s,
         "voxels_per_s": V / (f_s * 1e-3), "bytes_per_voxel": 8,
         "vs_unfused_module_chain": (res["cage_warp"]["chain"]["fwd_ms"] + res["cage_warp"]["chain"]["bwd_ms"] + (c_s - f_f - f_b)) / f_s}
+    # VOLSTN_FAST_ARITH (tolerance mode: out within 1e-5 max|out| of the chain): the brick kernels of csrc/cagebrick.cu
+    fast, fstep = vnn.CageWarpVolumetric(onlyGrid=True, fastArith=True), vnn.CageWarpSmoothL1Volumetric(fastArith=True)
+    idc = rep(synth.alignet_cage(nb, 8, rng, jitter=0.0).astype(np.float32))
+    ff_f, ff_b = timed(lambda: fast.updateOutput([vol, cage])), timed(lambda: fast.updateGradInput([vol, cage], go))
+    ff_s, ff_si = timed(lambda: fstep.forwardBackward([vol, cage], target)), timed(lambda: fstep.forwardBackward([vol, idc], target))
+    res["cage_warp"]["fast_arith"] = {"fwd_ms": ff_f, "bwd_ms": ff_b, "voxels_per_s": V / ((ff_f + ff_b) * 1e-3),
+                                      "calls": "the same entry points with VOLSTN_FAST_ARITH (brick kernels)"}
+    res["cage_warp_step"]["fast_arith"] = {
+        "one_kernel_ms": ff_s, "voxels_per_s": V / (ff_s * 1e-3), "speedup_over_exact": f_s / ff_s,
+        "identity_cage_ms": ff_si, "identity_cage_voxels_per_s": V / (ff_si * 1e-3),
+        "note": "jittered cage (sheared field: ~18 L1 sectors per gather) and the identity cage ALIGNet starts from (weight 0 / bias del, models/alignet_2d.lua:118-119)"}
+    del idc
     # the same one-kernel step for the plain sampler (a dense field tensor), identity field
     gridn0 = rep(synth.grid("g1", nb, N, N, N, rng))
     smp_og, sstep = vnn.BilinearSamplerVolumetric(onlyGrid=True), vnn.BilinearSamplerSmoothL1Volumetric()

@@ -106,14 +106,18 @@ typedef struct volstn_tensor5 {
 #define VOLSTN_DEBUG_NO_FAST 0x10000u   /* every warp takes the exact predicated path            */
 #define VOLSTN_DEBUG_NO_BORDER 0x20000u /* warps touching a high face take the exact path (no border tier) */
 /* Cage entry points (volstn_b200_cage_warp_forward / _backward / _step), single-channel volumes: FAST ARITHMETIC.  The
- * cage up-sample is evaluated in its separable form (per output row the four (y, z) corners are folded into cW + 1
- * x-nodes once, then every voxel is one linear interpolation between two nodes), the eight-term sums are FMA chains
- * and gradGrid is factored per axis.  Same mathematics as the default path, different rounding: the up-sampled field
- * moves by a few ulp, so `out` is within 1e-5 * max|out| of the reference chain instead of bit-identical, and where a
- * sampling coordinate sits on a cell boundary (the identity cage: every voxel) the source warp may take the
- * neighbouring cell -- with an interpolation weight within a few ulp of 0 or 1, i.e. the same value, and the OTHER
- * one-sided derivative for gradCage (the function is only C0 there; the reference's own CUDA path differs from its
- * CPU path in the same way, its kernels being compiled with FMA contraction).  Off by default. */
+ * cage up-sample is evaluated in its separable form, the trilinear value and its three coordinate derivatives come from
+ * the seven nested linear interpolations, every sum is an FMA chain.  Same mathematics as the default path, different
+ * rounding: the up-sampled field moves by a few ulp, so `out` is within 1e-5 * max|out| of the reference chain instead
+ * of bit-identical, and where a sampling coordinate sits on a cell boundary (the identity cage: every voxel) the source
+ * warp may take the neighbouring cell -- with an interpolation weight within a few ulp of 0 or 1, i.e. the same value,
+ * and the OTHER one-sided derivative for gradCage (the function is only C0 there; the reference's own CUDA path differs
+ * from its CPU path in the same way, its kernels being compiled with FMA contraction).  That includes the LOW faces of
+ * the source volume: a coordinate less than size * 2^-23 (a few ulp) below 0 is read as 0.
+ * Kernels: contiguous tensors (the training case) run the brick kernels of csrc/cagebrick.cu -- a warp per cage cell and
+ * 32-wide x slot, the cage folded along x per task and along z per z, the gradient folded back the same way -- other
+ * layouts the row kernels of csrc/rowwarp.cu with the same contract (VOLSTN_ALGO_ROW forces them, for A/B timing).
+ * Off by default. */
 #define VOLSTN_FAST_ARITH 0x40000u
 /* voxels per thread (bits 12..15), 0 = automatic */
 #define VOLSTN_VPT_SHIFT 12

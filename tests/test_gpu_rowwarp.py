@@ -595,6 +595,82 @@ def test_fast_arith_cage_warp_within_tolerance_of_the_chain(cdims, oshape):
     # -- which is the point: the value is continuous across a cell boundary.
 
 
+@pytest.mark.parametrize("cdims,oshape,ishape", [((4, 4, 4), (16, 16, 16), None), ((1, 4, 3), (5, 9, 33), (6, 7, 8)),
+                                                 ((3, 1, 2), (8, 5, 70), (4, 9, 5)), ((2, 2, 1), (6, 6, 6), (1, 5, 7)),
+                                                 ((8, 8, 8), (64, 64, 64), (32, 32, 32)), ((5, 6, 7), (12, 40, 31), (128, 128, 9))])
+def test_fast_arith_brick_kernels_padding_tiers_and_degenerate_cages(cdims, oshape, ishape):
+    """The brick kernels (csrc/cagebrick.cu: contiguous tensors + VOLSTN_FAST_ARITH) where their two tiers and their
+    table remapping are stressed: cages far outside the volume (general tier: clamped, shifted floor, predicated corners =
+    the reference's zero padding ...c:542-564), folded cages, one-node cage axes, one-voxel source axes, a source
+    resolution different from the output's (run-time and compile-time strides), ragged x slots.  Against the oracle
+    chain at the tolerance of the mode, and against the row kernels in the same mode (VOLSTN_ALGO_ROW)."""
+    rng = np.random.default_rng(23 + cdims[0] + oshape[2])
+    B = 4
+    ishape = ishape or oshape
+    src = np.ascontiguousarray(synth.volume("v2", B, *[max(s, 2) for s in ishape], 1, rng)[:, :ishape[0], :ishape[1], :ishape[2]])
+    tshape = (B,) + oshape + (1,)
+    target = (rng.uniform(size=tshape) > 0.6).astype(np.float32)
+    cage = np.stack([synth.alignet_cage(1, max(max(cdims), 2), rng)[0][:, :cdims[0], :cdims[1], :cdims[2]] for _ in range(B)]).astype(np.float32)
+    cage[1] *= 2.5                                                              # most of the field far outside the volume
+    cage[2] = rng.uniform(-1.6, 1.6, cage[2].shape).astype(np.float32)          # folded, partly outside
+    cage[3] = np.clip(cage[3], -1.0, 1.0)                                       # faces hit exactly
+    go = rng.standard_normal(tshape).astype(np.float32)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    # a coordinate is known to a few ulp of the source extent: the tolerance of the mode scales with it beyond 64 voxels
+    scale = max(1e-30, float(np.max(np.abs(ref_out)))) * max(1.0, max(ishape) / 64.0)
+    for algo in (0, _abi.ALGO_ROW):
+        m = vnn.CageWarpVolumetric(*oshape, fastArith=True, algo=algo)
+        out = host(m.updateOutput([dev(src), dev(cage)]))
+        assert np.isfinite(out).all()
+        assert float(np.max(np.abs(out - ref_out))) <= 3e-5 * scale, (algo, float(np.max(np.abs(out - ref_out))) / scale)
+        gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+        assert max_rel(host(gsrc), ref_gsrc) <= 1e-4, algo
+        err = np.abs(host(gcage) - ref_gcage) / max(1e-30, float(np.max(np.abs(ref_gcage))))
+        assert float(np.mean(err <= 1e-4)) >= 0.9 and float(err.max()) <= 8e-2, (algo, float(np.mean(err <= 1e-4)), float(err.max()))
+    # the two kernel families agree with each other much more closely than either has to agree with the chain
+    a_out = host(vnn.CageWarpVolumetric(*oshape, fastArith=True).updateOutput([dev(src), dev(cage)]))
+    r_out = host(vnn.CageWarpVolumetric(*oshape, fastArith=True, algo=_abi.ALGO_ROW).updateOutput([dev(src), dev(cage)]))
+    assert float(np.max(np.abs(a_out - r_out))) <= 3e-5 * scale
+    # the one-kernel step on the same inputs
+    ref_loss = oracle.smooth_l1_forward(ref_out, target, True)
+    g_o = oracle.smooth_l1_backward(ref_out, target, True)
+    _, _, ref_gc = cage_chain_oracle(src, cage, oshape, g_o)
+    ref_iou = oracle.iou_counts(ref_out, target).astype(np.int64)
+    st = vnn.CageWarpSmoothL1Volumetric(fastArith=True, keepOutput=True)
+    loss, (_, gc) = st.forwardBackward([dev(src), dev(cage)], dev(target))
+    assert float(np.max(np.abs(host(st.output) - ref_out))) <= 3e-5 * scale
+    assert abs(float(loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
+    err = np.abs(host(gc) - ref_gc) / max(1e-30, float(np.max(np.abs(ref_gc))))
+    assert float(np.mean(err <= 1e-4)) >= 0.9 and float(err.max()) <= 8e-2, (float(np.mean(err <= 1e-4)), float(err.max()))
+    iou = st.iouCounts.cpu().numpy().astype(np.int64)
+    assert np.all(np.abs(iou - ref_iou) <= np.maximum(2, ref_iou // 100000)), (iou, ref_iou)
+
+
+def test_fast_arith_brick_kernels_survive_non_finite_cages():
+    """NaN / Inf / huge cage nodes: the reference turns them into NaN outputs of the voxels they reach; the brick kernels
+    clamp the coordinate (NaN -> far outside = zero padding).  Claimed: no fault, every voxel the bad nodes do NOT reach
+    keeps its value, nothing non-finite leaks into the cage gradient of the other samples."""
+    rng = np.random.default_rng(41)
+    B, oshape, csz = 3, (16, 16, 40), 4
+    src = synth.volume("v2", B, *oshape, 1, rng)
+    cage = _jittered_cages(B, (csz, csz, csz), rng)
+    clean = cage.copy()
+    cage[1, 0, 1, 2, 1] = np.nan
+    cage[1, 2, 3, 3, 3] = np.inf
+    cage[1, 1, 0, 0, 0] = -3e38
+    go = synth.grad_output(B, *oshape, 1, rng)
+    m = vnn.CageWarpVolumetric(fastArith=True)
+    out = host(m.updateOutput([dev(src), dev(cage)]))
+    ref = host(vnn.CageWarpVolumetric(fastArith=True).updateOutput([dev(src), dev(clean)]))
+    assert np.isfinite(out).all()
+    assert np.array_equal(out[0], ref[0]) and np.array_equal(out[2], ref[2])
+    _, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
+    _, gclean = vnn.CageWarpVolumetric(fastArith=True).updateGradInput([dev(src), dev(clean)], dev(go))
+    g, gc = host(gcage), host(gclean)
+    assert np.isfinite(g[0]).all() and np.isfinite(g[2]).all()
+    assert max_rel(g[0], gc[0]) <= 1e-4 and max_rel(g[2], gc[2]) <= 1e-4
+
+
 def test_fast_arith_identity_cage_reproduces_the_source():
     """ALIGNet at initialisation: every sampling coordinate sits ON a cell boundary, so the fast path may read the
     neighbouring cell with a weight within rounding of 0 or 1 -- the VALUE is the source voxel either way."""
