@@ -16,10 +16,13 @@
 //     one red.global per (cell corner, channel) -- no shared memory, no staging, no per-row sums;
 //   * the trilinear value and its three coordinate derivatives come from the seven lerps of the separable form
 //     (22 flops instead of the reference's 8 + 7 and 40 + 21);
-//   * two tiers per warp and row: STRICT (every corner of every lane inside the volume: conversion-free floor, no
-//     predicates) and GENERAL (coordinates clamped to [-2, size + 1] and shifted by 2 so that the same floor trick
-//     applies; corners outside the volume are predicated off and read as the reference's zero padding,
-//     ...c:542-564, with zero value AND zero derivative beyond one voxel outside).
+//   * three tiers per warp and trip of rows, chosen by warp votes on one unsigned compare per axis: STRICT (every corner
+//     of every lane inside the volume; a coordinate a few ulp below 0 -- the identity cage's low faces -- is read as 0:
+//     conversion-free floor, no predicates), BORDER (0 <= c < size: in the last cell of an axis the high corner is the
+//     reference's zero padding, ...c:542-564 -- the identity cage puts a whole face exactly ON size - 1, where the
+//     reference takes that cell -- three predicates) and GENERAL (coordinates clamped to [-2, size + 1] and shifted by
+//     2 so that the same floor trick applies; corners outside the volume are predicated off: zero value AND zero
+//     derivative beyond one voxel outside).
 //
 // Same mathematics as the reference chain, different rounding: these kernels exist only behind VOLSTN_FAST_ARITH
 // (include/volstn_b200.h), whose guarantees are measured in tests/test_gpu_rowwarp.py::test_fast_arith_*.
@@ -43,7 +46,8 @@ struct BrickLane {
 // VS: 0 = run-time strides of the source volume, else iW = iH = VS (row and plane offsets are immediates of the loads)
 // The rows of a trip share one tier vote so that all their gathers are in flight together, and the target / gradOut
 // element of every row is requested before the vote.
-template <int MODE, bool GV, int VS, int NR, bool GENERAL>
+// TIER: 0 = strict (no predicates), 1 = border (high corners may lie in the padding), 2 = general
+template <int MODE, bool GV, int VS, int NR, int TIER>
 __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__restrict__ vb, const float (&c)[NR][3],
                                            const float (&wyh)[NR], const float (&tg)[NR], const float *__restrict__ tp,
                                            float *__restrict__ op, bool valid, BrickLane &L) {
@@ -54,7 +58,7 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
 #pragma unroll
   for (int r = 0; r < NR; r++) {
     int off;
-    if constexpr (GENERAL) {
+    if constexpr (TIER == 2) {
       // clamp to [-2, size + 1] (NaN -> -2), shift by 2: t in [0, size + 3], floor by the 2^23 trick; corner i0 = j - 2
       const float tz = __fadd_rn(fminf(fmaxf(c[r][0], -2.0f), a.cmz), 2.0f);
       const float ty = __fadd_rn(fminf(fmaxf(c[r][1], -2.0f), a.cmy), 2.0f);
@@ -79,7 +83,9 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
       f[r][0] = __fsub_rn(cz, __fsub_rn(rz, 8388608.0f));
       f[r][1] = __fsub_rn(cy, __fsub_rn(ry, 8388608.0f));
       f[r][2] = __fsub_rn(cx, __fsub_rn(rx, 8388608.0f));
-      zl[r] = zh[r] = yl[r] = yh[r] = xl[r] = xh[r] = true;
+      zl[r] = yl[r] = xl[r] = true;
+      // border tier: 0 <= c < size; in the last cell [size - 1, size) the high corner is the zero padding (...c:542-564)
+      zh[r] = TIER == 0 || cz < a.tz1, yh[r] = TIER == 0 || cy < a.ty1, xh[r] = TIER == 0 || cx < a.tx1;
       off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kstrict), wrap_mul(__float_as_int(ry), sH)),
                      __float_as_int(rx));
     }
@@ -90,7 +96,7 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
   for (int r = 0; r < NR; r++) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const bool in = !GENERAL || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
+      const bool in = TIER == 0 || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
       v[r][k] = in ? __ldg(p0[r] + (k & 1) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0)) : 0.0f;
     }
   }
@@ -140,7 +146,7 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
         if (valid) {
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            const bool in = !GENERAL || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
+            const bool in = TIER == 0 || (((k & 4) ? zh[r] : zl[r]) && ((k & 2) ? yh[r] : yl[r]) && ((k & 1) ? xh[r] : xl[r]));
             if (in) red_add(g0p + (k & 1) + ((k & 2) ? sH : 0) + ((k & 4) ? sD : 0), q[k >> 1] * ((k & 1) ? fx : ux));
           }
         }
@@ -155,22 +161,26 @@ __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__re
                                            const float (&D)[3], const float (&wyh)[NR], const float *__restrict__ tp,
                                            float *__restrict__ op, bool valid, BrickLane &L) {
   float c[NR][3], tg[NR];
-  bool strict = true;
+  bool strict = true, inside = true;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
 #pragma unroll
     for (int i = 0; i < 3; i++) c[r][i] = fmaf(wyh[r], D[i], C0[i]);
-    // -eps <= c < size - 1 on every axis: one unsigned compare per axis on the IEEE bits of c + eps (negative and NaN
-    // patterns are larger than any positive bound)
-    strict = strict & ((unsigned)__float_as_int(c[r][0] + a.ez) < a.ubz) & ((unsigned)__float_as_int(c[r][1] + a.ey) < a.uby) &
-             ((unsigned)__float_as_int(c[r][2] + a.ex) < a.ubx);
+    // strict: -eps <= c < size - 1 on every axis, inside: -eps <= c < size - eps: unsigned compares on the IEEE bits of
+    // c + eps (negative and NaN patterns are larger than any positive bound)
+    const unsigned uz = (unsigned)__float_as_int(c[r][0] + a.ez), uy = (unsigned)__float_as_int(c[r][1] + a.ey),
+                   ux = (unsigned)__float_as_int(c[r][2] + a.ex);
+    strict = strict & (uz < a.ubz) & (uy < a.uby) & (ux < a.ubx);
+    inside = inside & (uz < a.uiz) & (uy < a.uiy) & (ux < a.uix);
     tg[r] = 0.0f;
     if constexpr (MODE != 0) tg[r] = ld_stream_f1(tp + r * a.oW);
   }
   if (__all_sync(0xffffffffu, strict))
-    brick_body<MODE, GV, VS, NR, false>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, VS, NR, 0>(a, vb, c, wyh, tg, tp, op, valid, L);
+  else if (__all_sync(0xffffffffu, inside))
+    brick_body<MODE, GV, VS, NR, 1>(a, vb, c, wyh, tg, tp, op, valid, L);
   else
-    brick_body<MODE, GV, VS, NR, true>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, VS, NR, 2>(a, vb, c, wyh, tg, tp, op, valid, L);
 }
 
 #ifndef BRICK_MIN_CTAS
@@ -377,12 +387,17 @@ void brick_plan(BrickArgs &a) {
   {
     const int sz[3] = {a.iD, a.iH, a.iW};
     float *eps[3] = {&a.ez, &a.ey, &a.ex};
-    unsigned *ub[3] = {&a.ubz, &a.uby, &a.ubx};
+    unsigned *ub[3] = {&a.ubz, &a.uby, &a.ubx}, *ui[3] = {&a.uiz, &a.uiy, &a.uix};
+    float *top[3] = {&a.tz1, &a.ty1, &a.tx1};
     for (int i = 0; i < 3; i++) {
       const float e = (float)sz[i] * 1.1920929e-7f, hi = (float)(sz[i] - 1) + e;
       *eps[i] = e;
-      *ub[i] = 0;  // a one-voxel axis has no cell: always the general tier
+      *ub[i] = 0;  // a one-voxel axis has no cell: never strict
       if (sz[i] > 1) memcpy(ub[i], &hi, 4);
+      // border tier: c + eps < size, i.e. the low corner exists (the high one may be the padding); top = size - 1
+      const float sizef = (float)sz[i];
+      memcpy(ui[i], &sizef, 4);
+      *top[i] = (float)(sz[i] - 1);
     }
   }
 }

@@ -24,6 +24,8 @@ struct BrickArgs {
   float hz, hy, hx;           // size + 1: high-corner bound of the shifted coordinate
   float ez, ey, ex;           // strict tier: -eps <= c < size - 1, eps = size * 2^-23 ...
   unsigned ubz, uby, ubx;     // ... as the exclusive bound on the IEEE bits of c + eps
+  unsigned uiz, uiy, uix;     // border tier: c + eps < size, same test
+  float tz1, ty1, tx1;        // size - 1: in the border tier a high corner exists iff c < size - 1
   int kstrict, kgen;          // constants that cancel the 2^23 exponent bits (and the shift) in the offset multiply-adds
   // training step
   float loss_norm;

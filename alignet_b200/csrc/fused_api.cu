@@ -162,6 +162,24 @@ int zero_grad_vol(const volstn_tensor5 *gradVol, cudaStream_t st) {
 }
 
 
+// the accumulators of a training step -- gradCage (floats), the per-sample loss sums (doubles) and IoU counts (64-bit) --
+// zeroed by ONE launch instead of three memset nodes (about 10 us of a 160 us step when the calls are not graph-captured)
+__global__ void k_zero_step(float *gcage, size_t ncage, double *loss, unsigned long long *iou, int B) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < ncage; k += stride) gcage[k] = 0.f;
+  if (i < (size_t)B) loss[i] = 0.0;
+  if (iou && i < 2 * (size_t)B) iou[i] = 0ull;
+}
+
+int zero_step(float *gcage, size_t ncage, double *loss, uint64_t *iou, int64_t B, cudaStream_t st) {
+  size_t need = ncage > 2 * (size_t)B ? ncage : 2 * (size_t)B;
+  unsigned blocks = (unsigned)((need + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < (unsigned)((2 * B + 255) / 256)) blocks = (unsigned)((2 * B + 255) / 256);
+  k_zero_step<<<blocks, 256, 0, st>>>(gcage, ncage, loss, reinterpret_cast<unsigned long long *>(iou), (int)B);
+  return after_launch();
+}
+
 // VOLSTN_FAST_ARITH on contiguous single-channel tensors: the brick kernels (cagebrick.cu).  Returns false when they do
 // not apply (the row kernels take the call).  `outlike`: out (forward), gradOut (backward) or the target (step).
 bool brick_args(BrickArgs &k, unsigned flags, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
@@ -399,9 +417,7 @@ int volstn_b200_cage_warp_step(int dtype, const void *cage, const int64_t cage_d
   if (B == 0) return VOLSTN_OK;
   if (!gradCage || !loss_sum) return VOLSTN_ERR_ARG;
   const size_t cage_bytes = (size_t)B * 3 * cage_dims[0] * cage_dims[1] * cage_dims[2] * 4;
-  VOLSTN_CUDA_TRY(cudaMemsetAsync(gradCage, 0, cage_bytes, st));
-  VOLSTN_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, (size_t)B * sizeof(double), st));
-  if (iou_counts) VOLSTN_CUDA_TRY(cudaMemsetAsync(iou_counts, 0, (size_t)B * 2 * sizeof(uint64_t), st));
+  if ((rc = zero_step(static_cast<float *>(gradCage), cage_bytes / 4, loss_sum, iou_counts, B, st))) return rc;
   if (desc_numel(target) == 0) return VOLSTN_OK;
   if (!cage || (out && !out->data)) return VOLSTN_ERR_ARG;
   {
@@ -468,8 +484,7 @@ int volstn_b200_sampler_step(int dtype, int G, const volstn_tensor5 *vol, const 
   }
   if (B == 0) return VOLSTN_OK;
   if (!loss_sum) return VOLSTN_ERR_ARG;
-  VOLSTN_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, (size_t)B * sizeof(double), st));
-  if (iou_counts) VOLSTN_CUDA_TRY(cudaMemsetAsync(iou_counts, 0, (size_t)B * 2 * sizeof(uint64_t), st));
+  if ((rc = zero_step(nullptr, 0, loss_sum, iou_counts, B, st))) return rc;
   if (desc_numel(target) == 0) return VOLSTN_OK;
   if (out && !out->data) return VOLSTN_ERR_ARG;
   RowArgs a;

@@ -565,6 +565,12 @@ class AffineSamplerVolumetric(Module):
         return self.gradInput
 
 
+def _zeros_like_view(t: torch.Tensor) -> torch.Tensor:
+    """an all-zero tensor of t's shape that occupies one element (stride 0 everywhere): read-only by construction --
+    torch refuses in-place writes to it"""
+    return torch.zeros((), dtype=t.dtype, device=t.device).expand(t.shape)
+
+
 class CageWarpVolumetric(Module):
     """ALIGNet's warp sub-graph (models/alignet_2d.lua:136-147 with alignet.lua:4-39, lifted to 3-D) as ONE kernel:
 
@@ -628,19 +634,23 @@ class CageWarpVolumetric(Module):
         v, go = _vol_view(vol, self.layout), _vol_view(gradOutput, self.layout)
         d, h, w = self._out_dims(v)
         assert tuple(go.shape) == (v.size(0), d, h, w, v.size(4))
-        gv = torch.empty_like(vol)
+        # onlyGrid: gradSource is all zeros by definition -- a broadcast zero (no 4-bytes-per-voxel fill per call; the
+        # kernels never touch it).  Host tensors keep a real buffer (the host entry points copy into it).
+        lazy_zero = self.onlyGrid and vol.is_cuda
+        gv = _zeros_like_view(vol) if lazy_zero else torch.empty_like(vol)
         gcage = torch.empty_like(cage)
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
         flags = _abi.BWD_ZERO_GRADVOL | self._fast()
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
-            gv.zero_()
+            if not lazy_zero:
+                gv.zero_()
         if vol.is_cuda:
             _require_device(vol.device.index)
             with torch.cuda.device(vol.device):
                 rc = _abi.lib().volstn_b200_cage_warp_backward(_dtype_code(vol), cage.data_ptr(), dims, _desc(v),
-                                                               _desc(_vol_view(gv, self.layout)), gcage.data_ptr(), _desc(go),
-                                                               flags, _stream(vol))
+                                                               None if lazy_zero else _desc(_vol_view(gv, self.layout)),
+                                                               gcage.data_ptr(), _desc(go), flags, _stream(vol))
         else:
             assert self.layout == "BDHWC", "host tensors: channels-last only"
             goc = go if go.is_contiguous() else go.contiguous()
@@ -686,21 +696,21 @@ class CageWarpSmoothL1Volumetric(Module):
         if self.keepOutput and out is None:
             target = target.contiguous()
             out = torch.empty_like(target)
-        gv = torch.empty_like(vol)
+        gv = _zeros_like_view(vol) if self.onlyGrid else torch.empty_like(vol)   # onlyGrid: a broadcast zero, never written
         gcage = torch.empty_like(cage)
         loss_sum = torch.empty((B,), dtype=torch.float64, device=vol.device)
         iou = torch.empty((B, 2), dtype=torch.int64, device=vol.device)
         # THNN: norm = sizeAverage ? 1. / ((real)nElement) : 1.  (double division, stored in `real`)
-        norm = float(torch.tensor(1.0 / float(torch.tensor(float(n), dtype=torch.float32)), dtype=torch.float32)) if self.sizeAverage else 1.0
+        norm = ctypes.c_float(1.0 / ctypes.c_float(float(n)).value).value if self.sizeAverage else 1.0
         dims = (ctypes.c_int64 * 3)(*[int(x) for x in cage.shape[2:]])
         flags = _abi.BWD_ZERO_GRADVOL | (_abi.FAST_ARITH if self.fastArith else 0) | (self.algo & 0xF00)
         if self.onlyGrid:
             flags |= _abi.BWD_ONLY_GRID
-            gv.zero_()
         _require_device(vol.device.index)
         with torch.cuda.device(vol.device):
             rc = _abi.lib().volstn_b200_cage_warp_step(_dtype_code(vol), cage.data_ptr(), dims, _desc(vol), _desc(target),
-                                                       _desc(out) if out is not None else None, _desc(gv), gcage.data_ptr(),
+                                                       _desc(out) if out is not None else None,
+                                                       None if self.onlyGrid else _desc(gv), gcage.data_ptr(),
                                                        loss_sum.data_ptr(), iou.data_ptr(), ctypes.c_float(norm), flags,
                                                        _stream(vol))
         _abi.check(rc, "CageWarpSmoothL1Volumetric_forwardBackward")

@@ -722,6 +722,29 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / k
 
+    def timed_graph(fn, k=K):
+        """one call captured in a CUDA graph and replayed k times: the device time of the call's launches without the
+        Python / ctypes overhead of the module wrapper (~0.1 ms per call, which hides kernels shorter than that)"""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
     vol = rep(synth.volume("v2", nb, N, N, N, 1, rng))
     go = torch.randn((B, N, N, N, 1), device="cuda")
 
@@ -790,9 +813,14 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
     ff_s, ff_si = timed(lambda: fstep.forwardBackward([vol, cage], target)), timed(lambda: fstep.forwardBackward([vol, idc], target))
     res["cage_warp"]["fast_arith"] = {"fwd_ms": ff_f, "bwd_ms": ff_b, "voxels_per_s": V / ((ff_f + ff_b) * 1e-3),
                                       "calls": "the same entry points with VOLSTN_FAST_ARITH (brick kernels)"}
+    g_x = timed_graph(lambda: step.forwardBackward([vol, cage], target))
+    g_s, g_si = timed_graph(lambda: fstep.forwardBackward([vol, cage], target)), timed_graph(lambda: fstep.forwardBackward([vol, idc], target))
+    res["cage_warp_step"]["one_kernel_graph_ms"] = g_x
     res["cage_warp_step"]["fast_arith"] = {
         "one_kernel_ms": ff_s, "voxels_per_s": V / (ff_s * 1e-3), "speedup_over_exact": f_s / ff_s,
         "identity_cage_ms": ff_si, "identity_cage_voxels_per_s": V / (ff_si * 1e-3),
+        "one_kernel_graph_ms": g_s, "identity_cage_graph_ms": g_si, "graph_speedup_over_exact": g_x / g_s,
+        "graph_note": "the same calls captured in a CUDA graph and replayed: device time without the module wrapper's Python overhead",
         "note": "jittered cage (sheared field: ~18 L1 sectors per gather) and the identity cage ALIGNet starts from (weight 0 / bias del, models/alignet_2d.lua:118-119)"}
     del idc
     # the same one-kernel step for the plain sampler (a dense field tensor), identity field
