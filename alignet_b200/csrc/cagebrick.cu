@@ -43,15 +43,14 @@ struct BrickLane {
 };
 
 // MODE: 0 = forward (store out), 1 = backward from gradOut, 2 = training step (SmoothL1 + IoU + backward, optional out)
-// VS: 0 = run-time strides of the source volume, else iW = iH = VS (row and plane offsets are immediates of the loads)
 // The rows of a trip share one tier vote so that all their gathers are in flight together, and the target / gradOut
 // element of every row is requested before the vote.
 // TIER: 0 = strict (no predicates), 1 = border (high corners may lie in the padding), 2 = general
-template <int MODE, bool GV, int VS, int NR, int TIER>
+template <int MODE, bool GV, int NR, int TIER>
 __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__restrict__ vb, const float (&c)[NR][3],
                                            const float (&wyh)[NR], const float (&tg)[NR], const float *__restrict__ tp,
                                            float *__restrict__ op, bool valid, BrickLane &L) {
-  const int sH = VS ? VS : a.iW, sD = VS ? VS * VS : a.iH * a.iW;
+  const int sH = a.iW, sD = a.iH * a.iW;
   float f[NR][3];
   const float *p0[NR];
   bool zl[NR], zh[NR], yl[NR], yh[NR], xl[NR], xh[NR];
@@ -156,7 +155,7 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
 }
 
 // C0[c]: the voxel coordinate (source voxel units) at the low y corner of the row's cage cell, D[c] = high - low
-template <int MODE, bool GV, int VS, int NR>
+template <int MODE, bool GV, int NR>
 __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__restrict__ vb, const float (&C0)[3],
                                            const float (&D)[3], const float (&wyh)[NR], const float *__restrict__ tp,
                                            float *__restrict__ op, bool valid, BrickLane &L) {
@@ -176,11 +175,11 @@ __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__re
     if constexpr (MODE != 0) tg[r] = ld_stream_f1(tp + r * a.oW);
   }
   if (__all_sync(0xffffffffu, strict))
-    brick_body<MODE, GV, VS, NR, 0>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, NR, 0>(a, vb, c, wyh, tg, tp, op, valid, L);
   else if (__all_sync(0xffffffffu, inside))
-    brick_body<MODE, GV, VS, NR, 1>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, NR, 1>(a, vb, c, wyh, tg, tp, op, valid, L);
   else
-    brick_body<MODE, GV, VS, NR, 2>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, NR, 2>(a, vb, c, wyh, tg, tp, op, valid, L);
 }
 
 #ifndef BRICK_MIN_CTAS
@@ -190,7 +189,7 @@ __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__re
 #define BRICK_NR 2
 #endif
 
-template <int MODE, bool GV, int VS>
+template <int MODE, bool GV>
 __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(const BrickArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BrickSmem m;
@@ -269,11 +268,11 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
       float wyh[BRICK_NR];
 #pragma unroll
       for (int r = 0; r < BRICK_NR; r++) wyh[r] = m.wy[y + r].y;
-      brick_rows<MODE, GV, VS, BRICK_NR>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, BRICK_NR>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
     }
     for (; y < yb; y++, eo += a.oW) {
       const float wyh[1] = {m.wy[y].y};
-      brick_rows<MODE, GV, VS, 1>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, 1>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
     }
     if constexpr (MODE != 0) {
       // c = C0 + wy_hi (C1 - C0): d/dC1 = T1, d/dC0 = T0 - T1; C_j = F_j h + h and F_j = P_j0 + wz_hi (P_j1 - P_j0)
@@ -402,11 +401,11 @@ void brick_plan(BrickArgs &a) {
   }
 }
 
-template <int MODE, bool GV, int VS>
-static int brick_launch_v(const BrickArgs &a, cudaStream_t st) {
+template <int MODE, bool GV>
+static int brick_launch_t(const BrickArgs &a, cudaStream_t st) {
   const size_t smem = brick_smem_bytes(a);
   if (smem > 48 * 1024)
-    VOLSTN_CUDA_TRY(cudaFuncSetAttribute(k_cage_brick<MODE, GV, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VOLSTN_CUDA_TRY(cudaFuncSetAttribute(k_cage_brick<MODE, GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = (a.ntask + kBrickWarps - 1) / kBrickWarps;
   const long long cplane = 3LL * a.cD * a.cH * a.cW, oplane = (long long)a.oD * a.oH * a.oW;
   for (int b0 = 0; b0 < a.B; b0 += 65535) {
@@ -419,21 +418,11 @@ static int brick_launch_v(const BrickArgs &a, cudaStream_t st) {
     if (c.out) c.out += (long long)b0 * oplane;
     if (c.loss) c.loss += b0;
     if (c.iou) c.iou += 2LL * b0;
-    k_cage_brick<MODE, GV, VS><<<dim3(nblk, nb), kBrickThreads, smem, st>>>(c);
+    k_cage_brick<MODE, GV><<<dim3(nblk, nb), kBrickThreads, smem, st>>>(c);
     int rc = after_launch();
     if (rc) return rc;
   }
   return VOLSTN_OK;
-}
-
-template <int MODE, bool GV>
-static int brick_launch_t(const BrickArgs &a, cudaStream_t st) {
-  if (a.iW == a.iH && !getenv("VOLSTN_BRICK_NO_VS")) {
-    if (a.iW == 32) return brick_launch_v<MODE, GV, 32>(a, st);
-    if (a.iW == 64) return brick_launch_v<MODE, GV, 64>(a, st);
-    if (a.iW == 128) return brick_launch_v<MODE, GV, 128>(a, st);
-  }
-  return brick_launch_v<MODE, GV, 0>(a, st);
 }
 
 int brick_launch(const BrickArgs &a, int mode, bool grad_vol, cudaStream_t st) {

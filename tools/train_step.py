@@ -55,6 +55,8 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
     """The training step on an ALREADY initialised process group (bench.py --config train and the bench line's `train`
     section call this; main() below is the stand-alone launcher).  Returns the result dict on every rank."""
     N, csz = size, 4
+    if os.environ.get("VOLSTN_TRAIN_CUDNN_BENCHMARK", "1") != "0":
+        torch.backends.cudnn.benchmark = True       # let cuDNN time its Conv3d algorithms once (library code, not product)
     lo, hi = shard.batch_slice(global_batch, world, rank)
     B = hi - lo
     torch.manual_seed(0)                                                # identical weights on every rank
@@ -69,7 +71,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
         gen = vnn.VolumetricGridGenerator(N, N, N)
         field_i = gen.updateOutput(torch.eye(4, device="cuda").repeat(B, 1, 1))     # constant, like fieldI (dataset_2d.lua:128)
     up, warp = vnn.BilinearSamplerVolumetric(), vnn.BilinearSamplerVolumetric()
-    fwarp, fstep = vnn.CageWarpVolumetric(), vnn.CageWarpSmoothL1Volumetric()
+    fwarp, fstep = vnn.CageWarpVolumetric(), vnn.CageWarpSmoothL1Volumetric(fastArith=(fused == 3))
     params = [p for p in net.parameters()]
     crit = tnn.SmoothL1Loss()
     ones = torch.ones((B, csz, csz, csz, 1), device="cuda")
@@ -91,7 +93,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
         cage = net(pair)                                                            # B x 3 x csz^3
         mark(timed, "cnn_fwd", 1)
         mark(timed, "warp", 0)
-        if fused == 2:                                                              # warp + criterion + both backwards: one kernel
+        if fused >= 2:                                                              # warp + criterion + both backwards: one kernel
             loss = vag.cage_warp_smooth_l1(src, cage.contiguous(), tgt, fstep)
         else:
             if fused == 1:
@@ -132,7 +134,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
         dist.barrier()
         ms = shard.max_over_ranks(ms, device="cuda")
     # where the step goes: one more step with events around its stages (device time of each stage on this rank; for
-    # fused = 2 "warp" is forward + criterion + the warp's backward in one kernel and "cnn_bwd" the CNN's backward alone)
+    # fused >= 2 "warp" is forward + criterion + the warp's backward in one kernel and "cnn_bwd" the CNN's backward alone)
     parts = {k: 0.0 for k in ev}
     reps = 3
     for _ in range(reps):
@@ -158,7 +160,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--global-batch", type=int, default=64); ap.add_argument("--size", type=int, default=64)
-    ap.add_argument("--fused", type=int, default=0, help="0: un-fused modules; 1: CageWarpVolumetric + torch criterion; 2: the one-kernel step")
+    ap.add_argument("--fused", type=int, default=0, help="0: un-fused modules; 1: CageWarpVolumetric + torch criterion; 2: the one-kernel step; 3: the same in fast arithmetic (brick kernels)")
     a = ap.parse_args()
     out_fd = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)                   # stdout = the JSON line only
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
