@@ -933,32 +933,38 @@ def run_fused(a, torch, vnn, synth, _abi, peak):
     dd = torch.from_numpy(np.abs(delta * (1 + 0.25 * rng.standard_normal((Bp, 3, csz, csz, csz)))).astype(np.float32)).cuda()
     src = torch.from_numpy(synth.volume("v2", Bp, Np, Np, Np, 1, rng)).cuda()
     gop = torch.from_numpy(synth.grad_output(Bp, Np, Np, Np, 1, rng)).cuda()
-    csp, cw = vnn.Cumsum(), vnn.CageWarpVolumetric(onlyGrid=True)
-
-    def pipeline():
-        cage_p = csp.updateOutput(dd) + (-1.0 - delta)
-        cw.updateOutput([src, cage_p])
-        _, gcage = cw.updateGradInput([src, cage_p], gop)
-        csp.updateGradInput(dd, gcage)
-
-    for _ in range(3):
-        pipeline()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        pipeline()
-    g.replay()
+    csp = vnn.Cumsum()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = statistics.median(ts)
+
+    def pipeline_ms(cw):
+        def pipeline():
+            cage_p = csp.updateOutput(dd) + (-1.0 - delta)
+            cw.updateOutput([src, cage_p])
+            _, gcage = cw.updateGradInput([src, cage_p], gop)
+            csp.updateGradInput(dd, gcage)
+
+        for _ in range(3):
+            pipeline()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            pipeline()
+        g.replay()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    ms = pipeline_ms(vnn.CageWarpVolumetric(onlyGrid=True))
+    ms_fast = pipeline_ms(vnn.CageWarpVolumetric(onlyGrid=True, fastArith=True))
     res["pipeline_32_fused"] = {"ms": ms, "voxels_per_s": Bp * Np ** 3 / (ms * 1e-3),
+                                "fast_arith_ms": ms_fast, "fast_arith_voxels_per_s": Bp * Np ** 3 / (ms_fast * 1e-3),
                                 "workload": f"config 2 with the fused module: Cumsum + beta + CageWarpVolumetric forward, backward to the cage, "
-                                            f"Cumsum backward; {Np}^3 x batch {Bp}, CUDA graph replay, L2 flushed before each replay"}
+                                            f"Cumsum backward; {Np}^3 x batch {Bp}, CUDA graph replay, L2 flushed before each replay; "
+                                            f"fast_arith = the same with VOLSTN_FAST_ARITH (brick kernels)"}
     return res
 
 

@@ -4,9 +4,12 @@
  * (luaopen_libcuvolstn, init.cu:10-15) and the same function names in the `nn` table of torch.CudaTensor
  * (BilinearSamplerVolumetric.cu:1074-1088).  The launchers of the reference (…cu:695-742, 1009-1072, 179-228,
  * 511-575) become one call each into the device-pointer C ABI on THC's current stream (…cu:706): asynchronous, no
- * allocation, no synchronisation, nothing retained.  This file contains no device code; it is a .cu only because the
+ * allocation, no synchronisation (except the fused training step, which returns its loss), nothing retained.  This file
+ * contains no device code; it is a .cu only because the
  * reference's CMakeLists.txt builds `init.cu` with CUDA_ADD_LIBRARY.
  */
+#include <cuda_runtime.h>
+
 #include "luaT.h"
 #include "THC.h"
 
@@ -144,6 +147,124 @@ static int cunn_VolumetricGridGenerator_updateGradInput(lua_State *L) {
   return 1;
 }
 
+/* ---------------------------------------------------------------------------------------------------------
+ * The fused modules of ALIGNet's warp head (no single reference function: the sub-graph models/alignet_2d.lua:136-147 +
+ * models/alignet.lua:4-39 lifted to 3-D, and the step of train.lua:123-126 with model.lua:34 and util.lua:110-120).
+ * ------------------------------------------------------------------------------------------------------- */
+static void cunn_volstn_cage(lua_State *L, THCState *state, THCudaTensor *cage, THCudaTensor *source, int64_t dims[3]) {
+  int i;
+  (void)L;
+  if (THCudaTensor_nDimension(state, cage) != 5 || THCudaTensor_size(state, cage, 1) != 3 ||
+      THCudaTensor_size(state, cage, 0) != THCudaTensor_size(state, source, 0) || !THCudaTensor_isContiguous(state, cage))
+    THError("nn.CageWarp: cage must be a contiguous B x 3 x cD x cH x cW tensor");
+  for (i = 0; i < 3; i++) dims[i] = (int64_t)THCudaTensor_size(state, cage, i + 2);
+}
+
+/* nn.CageWarpVolumetric: (self, source, cage, output [, flags]) */
+static int cunn_CageWarpVolumetric_updateOutput(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *source = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *cage = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *output = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 5));
+  volstn_tensor5 v, o;
+  int64_t dims[3];
+  cunn_volstn_desc5(state, &v, source, "source");
+  cunn_volstn_desc5(state, &o, output, "output");
+  cunn_volstn_cage(L, state, cage, source, dims);
+  VOLSTN_GLUE_CHECK("CageWarpVolumetric.updateOutput",
+                    volstn_b200_cage_warp_forward(VOLSTN_F32, THCudaTensor_data(state, cage), dims, &v, &o, flags,
+                                                  (void *)THCState_getCurrentStream(state)));
+  return 1;
+}
+
+/* (self, source, cage, gradSource, gradCage, gradOutput [, flags]): gradCage is assigned; gradSource is accumulated into
+ * (VOLSTN_BWD_ZERO_GRADVOL zero-fills it first) and ignored with VOLSTN_BWD_ONLY_GRID */
+static int cunn_CageWarpVolumetric_updateGradInput(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *source = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *cage = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *gradSource = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  THCudaTensor *gradCage = (THCudaTensor *)luaT_checkudata(L, 5, "torch.CudaTensor");
+  THCudaTensor *gradOutput = (THCudaTensor *)luaT_checkudata(L, 6, "torch.CudaTensor");
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 7));
+  volstn_tensor5 v, gv, go;
+  int64_t dims[3];
+  cunn_volstn_desc5(state, &v, source, "source");
+  cunn_volstn_desc5(state, &go, gradOutput, "gradOutput");
+  cunn_volstn_cage(L, state, cage, source, dims);
+  if (!THCudaTensor_isContiguous(state, gradCage) || THCudaTensor_nElement(state, gradCage) != THCudaTensor_nElement(state, cage))
+    THError("nn.CageWarp: gradCage must be contiguous and of the cage's size");
+  if (!(flags & VOLSTN_BWD_ONLY_GRID)) cunn_volstn_desc5(state, &gv, gradSource, "gradSource");
+  VOLSTN_GLUE_CHECK("CageWarpVolumetric.updateGradInput",
+                    volstn_b200_cage_warp_backward(VOLSTN_F32, THCudaTensor_data(state, cage), dims, &v,
+                                                   (flags & VOLSTN_BWD_ONLY_GRID) ? NULL : &gv, THCudaTensor_data(state, gradCage), &go,
+                                                   flags, (void *)THCState_getCurrentStream(state)));
+  return 1;
+}
+
+/* nn.CageWarpSmoothL1Volumetric: (self, source, cage, target, output, gradSource, gradCage, workspace, stats, gradScale [, flags]).
+ * One kernel: forward, SmoothL1Criterion and its gradient (gradScale = 1 / nElement with sizeAverage, THNN), the
+ * intersection / union counts at 0.5 and the backward.  `output` may be an EMPTY tensor (the forward value is then not
+ * stored).  `workspace` is a module-owned CudaTensor of at least 6 B + 2 floats (device accumulators: B doubles + 2 B 64-bit
+ * counts); `stats` is a module-owned HOST torch.DoubleTensor B x 3 that receives (SmoothL1 sum, intersection, union) per
+ * sample.  Like criterion:forward in train.lua:123, which returns a Lua number, the call synchronises with its stream. */
+static int cunn_CageWarpSmoothL1Volumetric_forwardBackward(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *source = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *cage = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *target = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  THCudaTensor *output = (THCudaTensor *)luaT_checkudata(L, 5, "torch.CudaTensor");
+  THCudaTensor *gradSource = (THCudaTensor *)luaT_checkudata(L, 6, "torch.CudaTensor");
+  THCudaTensor *gradCage = (THCudaTensor *)luaT_checkudata(L, 7, "torch.CudaTensor");
+  THCudaTensor *workspace = (THCudaTensor *)luaT_checkudata(L, 8, "torch.CudaTensor");
+  THDoubleTensor *stats = (THDoubleTensor *)luaT_checkudata(L, 9, "torch.DoubleTensor");
+  const float grad_scale = (float)lua_tonumber(L, 10);
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 11));
+  cudaStream_t st = (cudaStream_t)THCState_getCurrentStream(state);
+  volstn_tensor5 v, t, o, gv;
+  int64_t dims[3];
+  long B, b;
+  const int keep = THCudaTensor_nElement(state, output) > 0;
+  char *ws;
+  double *loss, *host;
+  uint64_t *iou;
+  cunn_volstn_desc5(state, &v, source, "source");
+  cunn_volstn_desc5(state, &t, target, "target");
+  cunn_volstn_cage(L, state, cage, source, dims);
+  B = THCudaTensor_size(state, source, 0);
+  if (keep) cunn_volstn_desc5(state, &o, output, "output");
+  if (!(flags & VOLSTN_BWD_ONLY_GRID)) cunn_volstn_desc5(state, &gv, gradSource, "gradSource");
+  if (!THCudaTensor_isContiguous(state, gradCage) || THCudaTensor_nElement(state, gradCage) != THCudaTensor_nElement(state, cage))
+    THError("nn.CageWarp: gradCage must be contiguous and of the cage's size");
+  if (THDoubleTensor_nDimension(stats) != 2 || THDoubleTensor_size(stats, 0) != B || THDoubleTensor_size(stats, 1) != 3 ||
+      !THDoubleTensor_isContiguous(stats))
+    THError("nn.CageWarpSmoothL1Volumetric: stats must be a contiguous B x 3 torch.DoubleTensor");
+  THCudaTensor_resize1d(state, workspace, 6 * B + 2);
+  ws = (char *)(((size_t)THCudaTensor_data(state, workspace) + 7) & ~(size_t)7);
+  loss = (double *)ws;
+  iou = (uint64_t *)(ws + 8 * (size_t)B);
+  VOLSTN_GLUE_CHECK("CageWarpSmoothL1Volumetric.forwardBackward",
+                    volstn_b200_cage_warp_step(VOLSTN_F32, THCudaTensor_data(state, cage), dims, &v, &t, keep ? &o : NULL,
+                                               (flags & VOLSTN_BWD_ONLY_GRID) ? NULL : &gv, THCudaTensor_data(state, gradCage), loss,
+                                               iou, grad_scale, flags, (void *)st));
+  host = (double *)malloc(24 * (size_t)(B > 0 ? B : 1));
+  if (!host) THError("nn.CageWarpSmoothL1Volumetric: out of memory");
+  if (cudaMemcpyAsync(host, ws, 24 * (size_t)B, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    free(host);
+    THError("nn.CageWarpSmoothL1Volumetric: reading the loss back failed");
+  }
+  for (b = 0; b < B; b++) {
+    double *row = THDoubleTensor_data(stats) + 3 * b;
+    const uint64_t *cnt = (const uint64_t *)(host + B) + 2 * b;
+    row[0] = host[b];
+    row[1] = (double)cnt[0];
+    row[2] = (double)cnt[1];
+  }
+  free(host);
+  return 1;
+}
+
 static const struct luaL_Reg cunn_BilinearSamplerVolumetric__[] = {
     {"BilinearSamplerVolumetric_updateOutput", cunn_BilinearSamplerVolumetric_updateOutput},
     {"BilinearSamplerVolumetric_updateGradInput", cunn_BilinearSamplerVolumetric_updateGradInput},
@@ -153,6 +274,9 @@ static const struct luaL_Reg cunn_BilinearSamplerVolumetric__[] = {
     {"Cumsum_updateGradInput", cunn_Cumsum_updateGradInput},
     {"VolumetricGridGenerator_updateOutput", cunn_VolumetricGridGenerator_updateOutput},
     {"VolumetricGridGenerator_updateGradInput", cunn_VolumetricGridGenerator_updateGradInput},
+    {"CageWarpVolumetric_updateOutput", cunn_CageWarpVolumetric_updateOutput},
+    {"CageWarpVolumetric_updateGradInput", cunn_CageWarpVolumetric_updateGradInput},
+    {"CageWarpSmoothL1Volumetric_forwardBackward", cunn_CageWarpSmoothL1Volumetric_forwardBackward},
     {NULL, NULL}};
 
 static void cunn_BilinearSamplerVolumetric_init(lua_State *L) { /* …cu:1083-1088 */

@@ -11,5 +11,9 @@ end
 require('volstn.VolumetricGridGenerator')
 require('volstn.BilinearSamplerVolumetric')
 require('volstn.Cumsum')
+if withCuda then
+   require('volstn.CageWarpVolumetric')            -- fused modules (CudaTensor only; INTEGRATION.md section 3)
+   require('volstn.CageWarpSmoothL1Volumetric')
+end
 
 return nn

@@ -21,7 +21,7 @@
  * exactly the reference's contract (gradInputImages accumulated into, inputs re-read by updateGradInput). */
 #define VOLSTN_GLUE_FLAG_MASK                                                                                     \
   (VOLSTN_BWD_ONLY_GRID | VOLSTN_BWD_ONLY_VOLUME | VOLSTN_BWD_ZERO_GRADVOL | VOLSTN_HOST_KEEP_INPUTS | \
-   VOLSTN_HOST_REUSE_INPUTS | VOLSTN_ALGO_MASK)
+   VOLSTN_HOST_REUSE_INPUTS | VOLSTN_ALGO_MASK | VOLSTN_FAST_ARITH)
 
 /* The reference's error convention (BilinearSamplerVolumetric.cu:736-740, 1066-1070): print, then THError. */
 #define VOLSTN_GLUE_CHECK(where, rc)                                                                  \

@@ -28,7 +28,7 @@ typedef struct value {
 } value;
 
 struct lua_State {
-  value arg[10];
+  value arg[16];
   int nargs;
   value stk[32];
   int top; /* entries in stk; stack index nargs + 1 + i */
@@ -208,7 +208,7 @@ const char *harness_error(lua_State *L) { return L->error; }
 
 void harness_args_clear(lua_State *L, int nargs) {
   int i;
-  for (i = 0; i < 10; i++) {
+  for (i = 0; i < 16; i++) {
     L->arg[i].kind = K_NIL;
     L->arg[i].p = NULL;
     L->arg[i].tname = NULL;

@@ -22,6 +22,9 @@ REFERENCE_NAMES = ["BilinearSamplerVolumetric_updateOutput", "BilinearSamplerVol
                    "BilinearSamplerBHWD_updateOutput", "BilinearSamplerBHWD_updateGradInput"]
 NEW_NAMES = ["Cumsum_updateOutput", "Cumsum_updateGradInput",
              "VolumetricGridGenerator_updateOutput", "VolumetricGridGenerator_updateGradInput"]
+# the fused modules of ALIGNet's warp head (lua/CageWarpVolumetric.lua, lua/CageWarpSmoothL1Volumetric.lua): CudaTensor only
+FUSED_NAMES = ["CageWarpVolumetric_updateOutput", "CageWarpVolumetric_updateGradInput",
+               "CageWarpSmoothL1Volumetric_forwardBackward"]
 
 
 class _THTensor(ctypes.Structure):  # layout of HARNESS_DECLARE_TENSOR in include/TH.h

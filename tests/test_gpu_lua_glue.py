@@ -175,3 +175,67 @@ def test_cumsum_and_grid_generator_functions(libs):
     small = luat.Tensor(torch.empty(4, device="cuda"))
     with pytest.raises(luat.LuaError, match="workspace tensor too small"):
         cuda.call("VolumetricGridGenerator_updateGradInput", gg, gT, small)
+
+
+def test_fused_cage_warp_functions(libs):
+    """lua/CageWarpVolumetric.lua / lua/CageWarpSmoothL1Volumetric.lua call three more functions of libcuvolstn; each is
+    driven through the fake stack with the module's slots and compared with the oracle chain of the un-fused reference
+    modules (bit-exact `out`; gradients at the tolerances of tests/test_gpu_rowwarp.py) -- in both arithmetic modes."""
+    from tests.test_gpu_rowwarp import cage_chain_oracle
+    _, cuda, _ = libs
+    rng = np.random.default_rng(19)
+    B, oshape, csz = 3, (9, 10, 37), 4
+    src = synth.volume("v2", B, *oshape, 1, rng)
+    tgt = synth.volume("v2", B, *oshape, 1, rng)
+    go = synth.grad_output(B, *oshape, 1, rng)
+    cage = np.stack([synth.alignet_cage(1, csz, rng)[0] for _ in range(B)]).astype(np.float32)
+    ref_out, ref_gsrc, ref_gcage = cage_chain_oracle(src, cage, oshape, go)
+    ts, tc, tt, tgo = (torch.from_numpy(x).cuda() for x in (src, cage, tgt, go))
+    ONLY_GRID, ZERO, FAST = _abi.BWD_ONLY_GRID, _abi.BWD_ZERO_GRADVOL, _abi.FAST_ARITH
+    for fast in (0, FAST):
+        out = torch.full((B, *oshape, 1), 7.0, device="cuda")
+        assert cuda.call("CageWarpVolumetric_updateOutput", ts, tc, out, ZERO | fast) == 1
+        if fast:
+            assert max_rel(out.cpu().numpy(), ref_out) <= 2e-5
+        else:
+            assert bits_equal(out.cpu().numpy(), ref_out)
+        gs, gc = torch.full_like(ts, 3.0), torch.full_like(tc, 3.0)
+        assert cuda.call("CageWarpVolumetric_updateGradInput", ts, tc, gs, gc, tgo, ZERO | fast) == 1
+        assert max_rel(gs.cpu().numpy(), ref_gsrc) <= 1e-4
+        err = np.abs(gc.cpu().numpy() - ref_gcage) / float(np.max(np.abs(ref_gcage)))
+        assert float(err.max()) <= (5e-2 if fast else 1e-4) and float(np.mean(err <= 1e-4)) >= 0.97
+        # onlyGrid: gradSource is an EMPTY tensor in the Lua module and is not touched
+        empty = torch.empty(0, device="cuda")
+        gc2 = torch.full_like(tc, 5.0)
+        assert cuda.call("CageWarpVolumetric_updateGradInput", ts, tc, empty, gc2, tgo, ZERO | ONLY_GRID | fast) == 1
+        assert max_rel(gc2.cpu().numpy(), gc.cpu().numpy()) <= 1e-5
+        # the one-kernel training step: workspace (device scratch) and stats (host DoubleTensor B x 3) are module-owned buffers
+        n = int(np.prod(tgt.shape))
+        ref_loss = oracle.smooth_l1_forward(ref_out, tgt, True)
+        _, _, ref_gc = cage_chain_oracle(src, cage, oshape, oracle.smooth_l1_backward(ref_out, tgt, True))
+        ref_iou = oracle.iou_counts(ref_out, tgt).astype(np.int64)
+        stats = np.full((B, 3), -1.0, np.float64)
+        ws = luat.Tensor(torch.empty(64, device="cuda"))
+        kept, gcs = torch.full((B, *oshape, 1), 9.0, device="cuda"), torch.full_like(tc, 9.0)
+        scale = float(np.float32(1.0 / np.float32(n)))
+        assert cuda.call("CageWarpSmoothL1Volumetric_forwardBackward", ts, tc, tt, kept, empty, gcs, ws, stats, scale,
+                         ZERO | ONLY_GRID | fast) == 1
+        loss = stats[:, 0].sum() / n
+        assert abs(loss - ref_loss) <= (1e-6 if fast else 1e-9) * max(1.0, abs(ref_loss))
+        iou = stats[:, 1:].astype(np.int64)
+        assert np.all(np.abs(iou - ref_iou) <= (2 if fast else 0)), (iou, ref_iou)
+        if fast:
+            assert max_rel(kept.cpu().numpy(), ref_out) <= 2e-5
+        else:
+            assert bits_equal(kept.cpu().numpy(), ref_out)
+        err = np.abs(gcs.cpu().numpy() - ref_gc) / float(np.max(np.abs(ref_gc)))
+        assert float(err.max()) <= (5e-2 if fast else 2e-4) and float(np.mean(err <= 2e-4)) >= 0.97
+        # keepOutput = false: an empty output tensor
+        stats2 = np.zeros((B, 3))
+        assert cuda.call("CageWarpSmoothL1Volumetric_forwardBackward", ts, tc, tt, empty, empty, gcs, ws, stats2, scale,
+                         ZERO | ONLY_GRID | fast) == 1
+        assert np.array_equal(stats2[:, 1:], stats[:, 1:]) and np.allclose(stats2[:, 0], stats[:, 0], rtol=1e-12, atol=0)   # double atomics: order
+    with pytest.raises(luat.LuaError, match="cage must be"):
+        cuda.call("CageWarpVolumetric_updateOutput", ts, tc[:, :2].contiguous(), torch.empty((B, *oshape, 1), device="cuda"))
+    with pytest.raises(luat.LuaError, match="stats must be"):
+        cuda.call("CageWarpSmoothL1Volumetric_forwardBackward", ts, tc, tt, empty, empty, gcs, ws, np.zeros((B, 2)), 1.0, ZERO | ONLY_GRID)
