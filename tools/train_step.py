@@ -51,7 +51,7 @@ class WarpNet(tnn.Module):
         return vag.cumsum(d.contiguous(), self.cumsum) + self.beta      # nn.Cumsum -> + beta (lua:102-112)
 
 
-def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
+def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1, graph=False):
     """The training step on an ALREADY initialised process group (bench.py --config train and the bench line's `train`
     section call this; main() below is the stand-alone launcher).  Returns the result dict on every rank."""
     N, csz = size, 4
@@ -61,7 +61,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
     B = hi - lo
     torch.manual_seed(0)                                                # identical weights on every rank
     net = WarpNet(csz).cuda()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=bool(graph))
     rng = np.random.default_rng(100 + rank)
     src = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()          # B x D x H x W x 1
     tgt = torch.from_numpy(synth.volume("v2", B, N, N, N, 1, rng)).cuda()
@@ -117,19 +117,44 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
         mark(timed, "adam", 1)
         return loss
 
+    if graph:
+        # Every step of a graph run -- the warm-ups included -- is issued on a side stream: autograd binds a parameter's
+        # gradient accumulator to the stream that was current when the parameter was first used, and an accumulator bound
+        # to the legacy default stream cannot take part in a capture.
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side)
     for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     n0 = _abi.launch_count()
+    step()
+    launches = _abi.launch_count() - n0
+    run_step = step
+    if graph:
+        # the whole step -- CNN forward, warp head, both backwards, the all-reduce, Adam -- as ONE CUDA graph: at 8 samples per
+        # GPU the eager step is bound by the ~150 kernel launches of the CNN, not by the GPU
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            static_loss = step()
+        torch.cuda.synchronize()
+
+        def run_step():
+            g.replay()
+            return static_loss
+        for _ in range(2):
+            run_step()
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = step()
+        loss = run_step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    launches = (_abi.launch_count() - n0) // steps
     if world > 1:
         dist.barrier()
         ms = shard.max_over_ranks(ms, device="cuda")
@@ -137,6 +162,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
     # fused >= 2 "warp" is forward + criterion + the warp's backward in one kernel and "cnn_bwd" the CNN's backward alone)
     parts = {k: 0.0 for k in ev}
     reps = 3
+    step(); torch.cuda.synchronize()       # after a capture the first eager step re-runs cuDNN's algorithm search: not timed
     for _ in range(reps):
         step(True); torch.cuda.synchronize()
         for k in ev:
@@ -149,7 +175,7 @@ def run(steps=10, warmup=3, global_batch=64, size=64, fused=2, rank=0, world=1):
     return {"config": "ALIGNet-3D training step (BASELINE.json config 3)", "size": N, "global_batch": global_batch,
             "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "samples_per_s": global_batch / (ms * 1e-3),
             "voxels_per_s": global_batch * N ** 3 / (ms * 1e-3), "loss": float(loss.detach()),
-            "stage_ms": parts, "largest_stage": limiter, "fused": fused, "volstn_kernels_per_step": int(launches),
+            "stage_ms": parts, "largest_stage": limiter, "fused": fused, "volstn_kernels_per_step": int(launches), "cuda_graph": bool(graph),
             "allreduce_floats": nparam if world > 1 else 0, "allreduce_us": parts["allreduce"] * 1e3, "scaling": "strong",
             "note": "CNN = plain PyTorch / cuDNN fp32 Conv3d (3-D lift of models/alignet_2d.lua:33-57; library code); Cumsum and the "
                     "warp head = this repo's kernels; one NCCL all-reduce of the CNN gradients per step (one flat buffer, .grad are views; "
@@ -161,13 +187,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--global-batch", type=int, default=64); ap.add_argument("--size", type=int, default=64)
     ap.add_argument("--fused", type=int, default=0, help="0: un-fused modules; 1: CageWarpVolumetric + torch criterion; 2: the one-kernel step; 3: the same in fast arithmetic (brick kernels)")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the whole step as one CUDA graph (stage_ms stay eager)")
     a = ap.parse_args()
     out_fd = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)                   # stdout = the JSON line only
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    res = run(a.steps, a.warmup, a.global_batch, a.size, a.fused, rank, world)
+    res = run(a.steps, a.warmup, a.global_batch, a.size, a.fused, rank, world, bool(a.graph))
     if rank == 0:
         print(json.dumps(res), file=out_fd, flush=True)
     if world > 1:
