@@ -252,49 +252,9 @@ __device__ __forceinline__ void cage_field_sep(const RowSmem &m, const float *nb
   xf = fmaf(wx, b0, wx1 * b1);
 }
 
-// The same with the lane's eight cage corners kept in registers (compile with -DROW_CAGE_CACHE=1): a lane's x (hence
-// its cage column) is the same for every row of a one-trip kernel and the row's cage cell (z0, y0) changes only
-// every few rows, so the eight 16-byte shared-memory loads (4 wavefronts each: the L1/LSU pipe is what bounds the
-// cage kernels, 87 % busy in profiles/r01_row_kernels.md) are needed for about one row in nine.  Measured on a B200
-// and REJECTED (profiles/r01_fbench_history.txt): the 48 extra registers either spill (caps of 64 / 80 registers:
-// forward 270 / 247 us against 199 us) or halve the occupancy (cap 128: forward 192 us, backward 455 us against 366 us).
-#ifndef ROW_CAGE_CACHE
-#define ROW_CAGE_CACHE 0
-#endif
-static_assert(!(ROW_CAGE_CACHE && ROW_CAGE_SPLIT), "the register-cached variant reads the 16-byte cells");
-struct CageCorners {
-  float vz[8], vy[8], vx[8];
-  int key;  // cell index of corner 0 the registers hold (-1: none)
-};
-__device__ __forceinline__ void cage_field_cached(const RowSmem &m, const RowArgs &a, int z, int y, int x, CageCorners &c,
-                                                  float &zf, float &yf, float &xf) {
-  const int cWp = a.cW + 1, cHWp = (a.cH + 1) * cWp;
-  const int base = (m.iz[z] * (a.cH + 1) + m.iy[y]) * cWp + m.ix[x];
-  if (base != c.key) {
-    const float4 *c0 = m.cg + base;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const float4 v = c0[(k & 1) + ((k >> 1) & 1) * cWp + (k >> 2) * cHWp];
-      c.vz[k] = v.x, c.vy[k] = v.y, c.vx[k] = v.z;
-    }
-    c.key = base;
-  }
-  const float wx = m.tx[x], wy = m.ty[y], wz = m.tz[z];
-  const float wxs[2] = {wx, __fsub_rn(1.0f, wx)};
-  const float wys[2] = {wy, __fsub_rn(1.0f, wy)};
-  const float wzs[2] = {wz, __fsub_rn(1.0f, wz)};
-  float az = 0.f, ay = 0.f, ax = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const float w = __fmul_rn(__fmul_rn(wxs[k & 1], wys[(k >> 1) & 1]), wzs[k >> 2]);
-    const float pz = __fmul_rn(w, c.vz[k]), py = __fmul_rn(w, c.vy[k]), px = __fmul_rn(w, c.vx[k]);
-    az = k ? __fadd_rn(az, pz) : pz;
-    ay = k ? __fadd_rn(ay, py) : py;
-    ax = k ? __fadd_rn(ax, px) : px;
-  }
-  zf = az, yf = ay, xf = ax;
-}
-
+// (Keeping the lane's eight cage corners in registers across rows was measured and rejected: 48 more registers spill or
+// halve the occupancy -- forward 192-270 us against 199 us, profiles/r01_fbench_history.txt.  The brick kernels of
+// cagebrick.cu get the same effect from their mapping.)
 template <int SRC, bool AOS4, bool FASTM = false>
 struct RowCoords {
   // per-CTA state of the source
@@ -326,14 +286,12 @@ struct RowCoords {
       __syncwarp();
     }
   }
-  CageCorners cc[(SRC == ROW_SRC_CAGE && ROW_CAGE_CACHE) ? 2 : 1];
   __device__ __forceinline__ void init(const RowArgs &a, int b) {
     if constexpr (SRC == ROW_SRC_AFFINE) {
 #pragma unroll
       for (int i = 0; i < 12; i++) t[i] = __ldg(a.T + (long long)b * 16 + i);
     }
     if constexpr (SRC == ROW_SRC_GRID) gb = opaque(a.s.grid + (long long)b * a.gB);
-    if constexpr (SRC == ROW_SRC_CAGE && ROW_CAGE_CACHE) cc[0].key = cc[1].key = -1;
   }
   template <int V>  // V: slot of the trip (compile time: the corner registers of the two slots are distinct)
   __device__ __forceinline__ void get(const RowSmem &m, const RowArgs &a, int z, int y, int x, float &zf, float &yf,
@@ -355,10 +313,7 @@ struct RowCoords {
       // V = slot of the trip: with two rows per trip slot 1 is the second row (clamped to the first at the end)
       cage_field_sep(m, nbuf + ((V && second_slot_row) ? 3 * nstride : 0), nstride, x, zf, yf, xf);
     } else {
-      if constexpr (ROW_CAGE_CACHE)
-        cage_field_cached(m, a, z, y, x, cc[V], zf, yf, xf);
-      else
-        cage_field(m, a, z, y, x, zf, yf, xf);
+      cage_field(m, a, z, y, x, zf, yf, xf);
     }
   }
   bool second_slot_row = false;  // set per trip by the kernels (TWO_ROWS and the second row exists)

@@ -101,8 +101,10 @@ def main():
         stp = vnn.CageWarpSmoothL1Volumetric(fastArith=True)
         report("cage STEP (fwd + SmoothL1 + IoU + bwd to the cage), fast arithmetic", timed(lambda: stp.forwardBackward([vol, cage], tgt)), 8 * V)
         idc = torch.from_numpy(synth.alignet_cage(nb, csz, rng, jitter=0.0).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
-        if True:
-            report("cage STEP, fast arithmetic, IDENTITY cage", timed(lambda: stp.forwardBackward([vol, idc], tgt)), 8 * V)
+        report("cage STEP, fast arithmetic, IDENTITY cage", timed(lambda: stp.forwardBackward([vol, idc], tgt)), 8 * V)
+        for jit in (0.02, 0.05, 0.1):
+            sc = torch.from_numpy(synth.alignet_cage(nb, csz, rng, jitter=jit).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
+            report(f"cage STEP, fast arithmetic, cage jitter {jit}", timed(lambda: stp.forwardBackward([vol, sc], tgt)), 8 * V)
 
     if "cage" in what:
         cage = torch.from_numpy(synth.alignet_cage(nb, csz, rng).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
