@@ -512,6 +512,23 @@ def test_fused_modules_match_the_reference_chain_golden():
         gsrc, gcage = m.updateGradInput([dev(src), dev(cage)], dev(go))
         assert max_rel(host(gsrc), c["gradSource"]) <= 1e-4, name
         assert max_rel(host(gcage), c["gradCage"]) <= 1e-4, name
+        # the same golden chains bound the tolerance mode (brick kernels: the golden tensors are contiguous, C = 1)
+        if src.shape[-1] == 1:
+            mf = vnn.CageWarpVolumetric(*oshape, fastArith=True)
+            scale = max(1.0, max(src.shape[1:4]) / 64.0)
+            assert max_rel(host(mf.updateOutput([dev(src), dev(cage)])), c["out"]) <= 5e-5 * scale, name
+            gsf, gcf = mf.updateGradInput([dev(src), dev(cage)], dev(go))
+            assert max_rel(host(gsf), c["gradSource"]) <= 1e-4, name
+            errf = np.abs(host(gcf) - c["gradCage"]) / max(1e-30, float(np.max(np.abs(c["gradCage"]))))
+            if name.startswith("identity"):
+                # The identity cage puts EVERY sampling coordinate on an integer, where the warp has two one-sided
+                # derivatives.  The reference's float arithmetic lands one ulp below the integer for about a third of
+                # the positions (left derivative) and on it for the rest (right derivative); the separable arithmetic
+                # lands exactly on it (always the right derivative).  On this binary volume the two differ by O(1), so
+                # no agreement of gradCage is claimed here (measured: 24 % of the cells within 1e-4) -- only sanity.
+                assert np.isfinite(host(gcf)).all()
+            else:
+                assert float(np.mean(errf <= 1e-4)) >= 0.9 and float(errf.max()) <= 8e-2, (name, float(np.mean(errf <= 1e-4)), float(errf.max()))
         if "step_loss" in c:
             step = vnn.CageWarpSmoothL1Volumetric(onlyGrid=False, keepOutput=True)  # output resolution = the target's
             loss, (gs, gc) = step.forwardBackward([dev(src), dev(cage)], dev(c["target"]))
