@@ -183,8 +183,8 @@ size_t volstn_b200_affine_sampler_backward_workspace(int64_t B, int64_t oD, int6
 int volstn_b200_cage_warp_forward(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
                                   const volstn_tensor5 *out, unsigned flags, void *cuda_stream);
 /* gradVol as for the sampler; gradCage (B x 3 x cD x cH x cW, ASSIGNED) = the cage up-sample's gradInput[1] of the
- * source warp's gradGrid.  VOLSTN_BWD_ONLY_GRID skips gradVol (the source is data, models/alignet_2d.lua:23-24),
- * VOLSTN_BWD_ONLY_VOLUME skips gradCage. */
+ * source warp's gradGrid.  VOLSTN_BWD_ONLY_GRID skips gradVol (the source is data, models/alignet_2d.lua:23-24): the
+ * descriptor is then not read and may be NULL (also in volstn_b200_cage_warp_step); VOLSTN_BWD_ONLY_VOLUME skips gradCage. */
 int volstn_b200_cage_warp_backward(int dtype, const void *cage, const int64_t cage_dims[3], const volstn_tensor5 *vol,
                                    const volstn_tensor5 *gradVol, void *gradCage, const volstn_tensor5 *gradOut,
                                    unsigned flags, void *cuda_stream);
