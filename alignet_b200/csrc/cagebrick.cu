@@ -268,11 +268,11 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
       float wyh[BRICK_NR];
 #pragma unroll
       for (int r = 0; r < BRICK_NR; r++) wyh[r] = m.wy[y + r].y;
-      brick_rows<MODE, GV, BRICK_NR>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, BRICK_NR>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
     }
     for (; y < yb; y++, eo += a.oW) {
       const float wyh[1] = {m.wy[y].y};
-      brick_rows<MODE, GV, 1>(a, vb, C0, D, wyh, tb + eo, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, 1>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
     }
     if constexpr (MODE != 0) {
       // c = C0 + wy_hi (C1 - C0): d/dC1 = T1, d/dC0 = T0 - T1; C_j = F_j h + h and F_j = P_j0 + wz_hi (P_j1 - P_j0)
