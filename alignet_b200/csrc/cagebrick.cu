@@ -7,13 +7,16 @@
 // arithmetic cheaper:
 //
 //   * a WARP owns a brick: one 32-wide x slot of the rows of ONE cage cell in y and (a part of) one cage cell in z.  A
-//     lane's x never changes, so its cage column (ix, wx) is a register constant, and the cell (kz, ky) is constant for
-//     the whole task: the twelve x-interpolated cage values  P[j][k][c] = wx.C[c][kz+k][ky+j][ix] + wx'.C[..][ix+1]  are
-//     formed ONCE per task, folded along z once per z (R[j][c], already in voxel units of the source volume) and a
-//     voxel's three sampling coordinates are two FMAs each;
-//   * the gradient takes the same road back: per voxel  S[j][c] += wy_j . (go . d out/d coord_c)  (six FMAs), per z
-//     A[j][k][c] += wz_k . S[j][c], and per TASK one segmented warp reduction over the lanes that share a cage column and
-//     one red.global per (cell corner, channel) -- no shared memory, no staging, no per-row sums;
+//     lane's x never changes, so its cage column (ix, wx) is a constant of the task, and so is the cell (kz, ky): the
+//     twelve x-interpolated cage values  P[j][k][c] = C[c][kz+k][ky+j][ix] + wx.(C[..][ix+1] - C[..][ix])  are formed ONCE
+//     per task (shared memory, [slot][thread]), folded along z and into voxel units of the source once per z
+//     (C0[c], D[c] = C1[c] - C0[c]: six registers) and a voxel's three sampling coordinates are ONE FMA each,
+//     c = C0 + wy.D.  The `low + w.(high - low)` form is exact where two nodes coincide: the identity cage yields
+//     coordinates ON the integers;
+//   * the gradient takes the same road back: per voxel  T0[c] += g_c, T1[c] += wy.g_c  with g = go . d out/d coord
+//     (six instructions), per z twelve FMAs into shared-memory accumulators A[j][k][c], and per TASK one segmented warp
+//     reduction over the lanes that share a cage column (consecutive lanes; shuffles by doubling) and one red.global per
+//     (cell corner, channel) -- no staging, no per-row sums;
 //   * the trilinear value and its three coordinate derivatives come from the seven lerps of the separable form
 //     (22 flops instead of the reference's 8 + 7 and 40 + 21);
 //   * three tiers per warp and trip of rows, chosen by warp votes on one unsigned compare per axis: STRICT (every corner
@@ -73,10 +76,10 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
       off = wrap_add(wrap_add(wrap_add(wrap_mul(__float_as_int(rz), sD), a.kgen), wrap_mul(__float_as_int(ry), sH)),
                      __float_as_int(rx));
     } else {
-      // -eps <= c < size - 1 on every axis.  A coordinate that rounding left a hair below 0 (the identity cage puts a
-      // whole face there) is read as 0: the value moves by less than eps x slope.  The HIGH face stays with the general
-      // tier: ON it the reference takes the cell outside (high corners in the zero padding, ...c:542-564), and the
-      // identity cage puts a whole face exactly there.
+      // strict: -eps <= c < size - 1 on every axis; border: -eps <= c < size.  A coordinate that rounding left a hair
+      // below 0 is read as 0: the value moves by less than eps x slope.  ON the high face (the identity cage puts a whole
+      // face exactly there) the reference takes the cell outside, high corners in the zero padding (...c:542-564): that
+      // is the border tier's predicate, never a clamp.
       const float cz = fmaxf(c[r][0], 0.0f), cy = fmaxf(c[r][1], 0.0f), cx = fmaxf(c[r][2], 0.0f);
       const float rz = __fadd_rd(cz, 8388608.0f), ry = __fadd_rd(cy, 8388608.0f), rx = __fadd_rd(cx, 8388608.0f);
       f[r][0] = __fsub_rn(cz, __fsub_rn(rz, 8388608.0f));
