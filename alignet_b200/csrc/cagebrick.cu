@@ -198,10 +198,14 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
   BrickSmem m;
   brick_fill(m, smem_raw, a);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.y;
+  // PERSISTENT warps: the axis tables above are built once per CTA (double divisions and two barriers: 10-15 % of a
+  // short-lived CTA), then every warp walks the task list of the whole batch with the stride of the launch; nothing
+  // below synchronises across warps.
+  const long long total = (long long)a.B * a.ntask;
+  for (long long task = (long long)blockIdx.x * kBrickWarps + wid; task < total; task += (long long)gridDim.x * kBrickWarps) {
+  const int b = (int)(task / a.ntask);
   // task -> (z unit, z part, y unit, y part, x slot); consecutive warps take consecutive x slots, then y
-  int t = blockIdx.x * kBrickWarps + wid;
-  if (t >= a.ntask) return;
+  int t = (int)(task - (long long)b * a.ntask);
   const int xs = t % a.nxs;
   t /= a.nxs;
   const int yp = t % a.ysplit;
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
     zb = za + (int)((long long)lz * (zp + 1) / a.zsplit), za += (int)((long long)lz * zp / a.zsplit);
     yb = ya + (int)((long long)ly * (yp + 1) / a.ysplit), ya += (int)((long long)ly * yp / a.ysplit);
   }
-  if (za >= zb || ya >= yb) return;
+  if (za >= zb || ya >= yb) continue;
 
   const int x = xs * 32 + lane;
   const bool valid = x < a.oW;
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
           }
         }
   }
+  }  // task loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -409,23 +414,16 @@ static int brick_launch_t(const BrickArgs &a, cudaStream_t st) {
   const size_t smem = brick_smem_bytes(a);
   if (smem > 48 * 1024)
     VOLSTN_CUDA_TRY(cudaFuncSetAttribute(k_cage_brick<MODE, GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblk = (a.ntask + kBrickWarps - 1) / kBrickWarps;
-  const long long cplane = 3LL * a.cD * a.cH * a.cW, oplane = (long long)a.oD * a.oH * a.oW;
-  for (int b0 = 0; b0 < a.B; b0 += 65535) {
-    BrickArgs c = a;
-    const int nb = a.B - b0 < 65535 ? a.B - b0 : 65535;
-    c.vol += (long long)b0 * a.vB;
-    c.cage += (long long)b0 * cplane;
-    if (c.gcage) c.gcage += (long long)b0 * cplane;
-    if (c.tgt) c.tgt += (long long)b0 * oplane;
-    if (c.out) c.out += (long long)b0 * oplane;
-    if (c.loss) c.loss += b0;
-    if (c.iou) c.iou += 2LL * b0;
-    k_cage_brick<MODE, GV><<<dim3(nblk, nb), kBrickThreads, smem, st>>>(c);
-    int rc = after_launch();
-    if (rc) return rc;
+  const long long need = ((long long)a.B * a.ntask + kBrickWarps - 1) / kBrickWarps;
+  long long nblk = need;
+  if (!getenv("VOLSTN_BRICK_NO_PERSIST")) {  // A/B timing only
+    const long long resident = (long long)kSMs * BRICK_MIN_CTAS;
+    if (nblk > resident) nblk = resident;
   }
-  return VOLSTN_OK;
+  if (nblk > 0x7fffffffLL) nblk = 0x7fffffffLL;
+  if (nblk < 1) return VOLSTN_OK;
+  k_cage_brick<MODE, GV><<<(unsigned)nblk, kBrickThreads, smem, st>>>(a);
+  return after_launch();
 }
 
 int brick_launch(const BrickArgs &a, int mode, bool grad_vol, cudaStream_t st) {

@@ -48,6 +48,21 @@ def main():
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / a.iters * 1e3
 
+    def timed_graph(fn):
+        """the call captured once in a CUDA graph and replayed: device time without the Python wrapper (~0.1 ms per call)"""
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2): fn()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g): fn()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters): g.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / a.iters * 1e3
+
     def report(name, us, alg_bytes=None, note=""):
         frac = f" {alg_bytes / us / 1e3:7.0f} GB/s alg ({alg_bytes / us / 1e3 / PEAK:5.1%})" if alg_bytes else ""
         print(f"{name:58s} {us:8.1f} us  {V / us / 1e3:6.1f} Gvox/s{frac}  {note}", flush=True)
@@ -102,6 +117,11 @@ def main():
         report("cage STEP (fwd + SmoothL1 + IoU + bwd to the cage), fast arithmetic", timed(lambda: stp.forwardBackward([vol, cage], tgt)), 8 * V)
         idc = torch.from_numpy(synth.alignet_cage(nb, csz, rng, jitter=0.0).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
         report("cage STEP, fast arithmetic, IDENTITY cage", timed(lambda: stp.forwardBackward([vol, idc], tgt)), 8 * V)
+        report("GRAPH cage fwd, fast arithmetic", timed_graph(lambda: fast.updateOutput([vol, cage])), 8 * V)
+        report("GRAPH cage bwd (gradCage only), fast arithmetic", timed_graph(lambda: fast.updateGradInput([vol, cage], go)), 8 * V)
+        report("GRAPH cage STEP, fast arithmetic", timed_graph(lambda: stp.forwardBackward([vol, cage], tgt)), 8 * V)
+        report("GRAPH cage STEP, fast arithmetic, IDENTITY cage", timed_graph(lambda: stp.forwardBackward([vol, idc], tgt)), 8 * V)
+        report("GRAPH cage fwd, fast arithmetic, IDENTITY cage", timed_graph(lambda: fast.updateOutput([vol, idc])), 8 * V)
         for jit in (0.02, 0.05, 0.1):
             sc = torch.from_numpy(synth.alignet_cage(nb, csz, rng, jitter=jit).astype(np.float32)).cuda().repeat(B // nb, 1, 1, 1, 1).contiguous()
             report(f"cage STEP, fast arithmetic, cage jitter {jit}", timed(lambda: stp.forwardBackward([vol, sc], tgt)), 8 * V)
