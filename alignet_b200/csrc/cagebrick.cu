@@ -188,8 +188,13 @@ __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__re
 #ifndef BRICK_MIN_CTAS
 #define BRICK_MIN_CTAS 3
 #endif
+// rows per trip: two for the kernels with a backward (three cost registers: step 163 -> 192 us), three for the forward
+// (identity cage 84.6 -> 77.8 us, jittered 140 -> 138 us); profiles/r02_fbench_brick_variants.txt
 #ifndef BRICK_NR
 #define BRICK_NR 2
+#endif
+#ifndef BRICK_NR_FWD
+#define BRICK_NR_FWD 3
 #endif
 
 template <int MODE, bool GV>
@@ -271,11 +276,12 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
     }
     unsigned eo = (unsigned)(z * a.oH + ya) * (unsigned)a.oW;
     int y = ya;
-    for (; y + BRICK_NR <= yb; y += BRICK_NR, eo += BRICK_NR * a.oW) {
-      float wyh[BRICK_NR];
+    constexpr int NRT = MODE == 0 ? BRICK_NR_FWD : BRICK_NR;
+    for (; y + NRT <= yb; y += NRT, eo += NRT * a.oW) {
+      float wyh[NRT];
 #pragma unroll
-      for (int r = 0; r < BRICK_NR; r++) wyh[r] = m.wy[y + r].y;
-      brick_rows<MODE, GV, BRICK_NR>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
+      for (int r = 0; r < NRT; r++) wyh[r] = m.wy[y + r].y;
+      brick_rows<MODE, GV, NRT>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
     }
     for (; y < yb; y++, eo += a.oW) {
       const float wyh[1] = {m.wy[y].y};
