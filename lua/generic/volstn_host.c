@@ -122,6 +122,51 @@ static int nn_(VolumetricGridGenerator_updateGradInput)(lua_State *L) {
 }
 
 /* the reference's four names first (generic/BilinearSamplerVolumetric.c:831-836), then the four new ones */
+/* ---- nn.AffineSamplerVolumetric on host tensors (the loader-side augmentation of dataset_2d.lua:285-311 and the projector
+ * of stn3dtorch/test.lua:15-25 run on CPU tensors): nn.VolumetricGridGenerator + nn.BilinearSamplerVolumetric in one call,
+ * the B x D x H x W x 4 grid never exists.  Float only (a new module; the reference's Double registration covers its four
+ * sampler functions).  (self, inputImages, T, output [, flags]) / (self, inputImages, T, gradInputImages, gradT, gradOutput
+ * [, flags]); T and gradT are contiguous B x 4 x 4. ---- */
+#if defined(TH_REAL_IS_FLOAT)
+static void nn_(volstn_affine_T)(THTensor *T, THTensor *images, const char *what) {
+  if (THTensor_(nDimension)(T) != 3 || THTensor_(size)(T, 1) != 4 || THTensor_(size)(T, 2) != 4 ||
+      THTensor_(size)(T, 0) != THTensor_(size)(images, 0) || !THTensor_(isContiguous)(T))
+    THError("%s: please input affine transform matrices (bx4x4)", what);
+}
+static int nn_(AffineSamplerVolumetric_updateOutput)(lua_State *L) {
+  THTensor *inputImages = (THTensor *)luaT_checkudata(L, 2, torch_Tensor);
+  THTensor *T = (THTensor *)luaT_checkudata(L, 3, torch_Tensor);
+  THTensor *output = (THTensor *)luaT_checkudata(L, 4, torch_Tensor);
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 5));
+  volstn_tensor5 v, o;
+  nn_(volstn_desc5)(&v, inputImages, "inputImages");
+  nn_(volstn_desc5)(&o, output, "output");
+  nn_(volstn_affine_T)(T, inputImages, "AffineSamplerVolumetric");
+  VOLSTN_GLUE_CHECK("AffineSamplerVolumetric.updateOutput",
+                    volstn_b200_host_affine_sampler_forward(volstn_glue_ctx(), VOLSTN_REAL_CODE, THTensor_(data)(T), &v, &o, flags));
+  return 1;
+}
+static int nn_(AffineSamplerVolumetric_updateGradInput)(lua_State *L) {
+  THTensor *inputImages = (THTensor *)luaT_checkudata(L, 2, torch_Tensor);
+  THTensor *T = (THTensor *)luaT_checkudata(L, 3, torch_Tensor);
+  THTensor *gradInputImages = (THTensor *)luaT_checkudata(L, 4, torch_Tensor);
+  THTensor *gradT = (THTensor *)luaT_checkudata(L, 5, torch_Tensor);
+  THTensor *gradOutput = (THTensor *)luaT_checkudata(L, 6, torch_Tensor);
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 7));
+  volstn_tensor5 v, gv, go;
+  nn_(volstn_desc5)(&v, inputImages, "inputImages");
+  nn_(volstn_desc5)(&go, gradOutput, "gradOutput");
+  nn_(volstn_affine_T)(T, inputImages, "AffineSamplerVolumetric");
+  nn_(volstn_affine_T)(gradT, inputImages, "AffineSamplerVolumetric (gradT)");
+  if (!(flags & VOLSTN_BWD_ONLY_GRID)) nn_(volstn_desc5)(&gv, gradInputImages, "gradInputImages");
+  VOLSTN_GLUE_CHECK("AffineSamplerVolumetric.updateGradInput",
+                    volstn_b200_host_affine_sampler_backward(volstn_glue_ctx(), VOLSTN_REAL_CODE, THTensor_(data)(T), &v,
+                                                             (flags & VOLSTN_BWD_ONLY_GRID) ? NULL : &gv, THTensor_(data)(gradT), &go,
+                                                             flags));
+  return 1;
+}
+#endif
+
 static const struct luaL_Reg nn_(BilinearSamplerVolumetric__)[] = {
     {"BilinearSamplerVolumetric_updateOutput", nn_(BilinearSamplerVolumetric_updateOutput)},
     {"BilinearSamplerVolumetric_updateGradInput", nn_(BilinearSamplerVolumetric_updateGradInput)},
@@ -131,6 +176,10 @@ static const struct luaL_Reg nn_(BilinearSamplerVolumetric__)[] = {
     {"Cumsum_updateGradInput", nn_(Cumsum_updateGradInput)},
     {"VolumetricGridGenerator_updateOutput", nn_(VolumetricGridGenerator_updateOutput)},
     {"VolumetricGridGenerator_updateGradInput", nn_(VolumetricGridGenerator_updateGradInput)},
+#if defined(TH_REAL_IS_FLOAT)
+    {"AffineSamplerVolumetric_updateOutput", nn_(AffineSamplerVolumetric_updateOutput)},
+    {"AffineSamplerVolumetric_updateGradInput", nn_(AffineSamplerVolumetric_updateGradInput)},
+#endif
     {NULL, NULL}};
 
 static void nn_(BilinearSamplerVolumetric_init)(lua_State *L) { /* ...c:838-843 */

@@ -265,6 +265,56 @@ static int cunn_CageWarpSmoothL1Volumetric_forwardBackward(lua_State *L) {
   return 1;
 }
 
+/* nn.AffineSamplerVolumetric on CudaTensors: (self, inputImages, T, output [, flags]) /
+ * (self, inputImages, T, gradInputImages, gradT, gradOutput, workspace [, flags]); `workspace` is a module-owned CudaTensor
+ * that is resized here (partial sums of the deterministic gradT reduction). */
+static void cunn_volstn_affine_T(THCState *state, THCudaTensor *T, THCudaTensor *images) {
+  if (THCudaTensor_nDimension(state, T) != 3 || THCudaTensor_size(state, T, 1) != 4 || THCudaTensor_size(state, T, 2) != 4 ||
+      THCudaTensor_size(state, T, 0) != THCudaTensor_size(state, images, 0) || !THCudaTensor_isContiguous(state, T))
+    THError("please input affine transform matrices (bx4x4)");
+}
+static int cunn_AffineSamplerVolumetric_updateOutput(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *inputImages = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *T = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *output = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 5));
+  volstn_tensor5 v, o;
+  cunn_volstn_desc5(state, &v, inputImages, "inputImages");
+  cunn_volstn_desc5(state, &o, output, "output");
+  cunn_volstn_affine_T(state, T, inputImages);
+  VOLSTN_GLUE_CHECK("AffineSamplerVolumetric.updateOutput",
+                    volstn_b200_affine_sampler_forward(VOLSTN_F32, THCudaTensor_data(state, T), &v, &o, flags,
+                                                       (void *)THCState_getCurrentStream(state)));
+  return 1;
+}
+static int cunn_AffineSamplerVolumetric_updateGradInput(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *inputImages = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *T = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *gradInputImages = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  THCudaTensor *gradT = (THCudaTensor *)luaT_checkudata(L, 5, "torch.CudaTensor");
+  THCudaTensor *gradOutput = (THCudaTensor *)luaT_checkudata(L, 6, "torch.CudaTensor");
+  THCudaTensor *ws = (THCudaTensor *)luaT_checkudata(L, 7, "torch.CudaTensor");
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 8));
+  volstn_tensor5 v, gv, go;
+  size_t bytes;
+  char *aligned;
+  cunn_volstn_desc5(state, &v, inputImages, "inputImages");
+  cunn_volstn_desc5(state, &go, gradOutput, "gradOutput");
+  cunn_volstn_affine_T(state, T, inputImages);
+  cunn_volstn_affine_T(state, gradT, inputImages);
+  if (!(flags & VOLSTN_BWD_ONLY_GRID)) cunn_volstn_desc5(state, &gv, gradInputImages, "gradInputImages");
+  bytes = volstn_b200_affine_sampler_backward_workspace(go.size[0], go.size[1], go.size[2], go.size[3]);
+  THCudaTensor_resize1d(state, ws, (long)((bytes + 3) / 4 + 2));
+  aligned = (char *)(((size_t)THCudaTensor_data(state, ws) + 7) & ~(size_t)7);
+  VOLSTN_GLUE_CHECK("AffineSamplerVolumetric.updateGradInput",
+                    volstn_b200_affine_sampler_backward(VOLSTN_F32, THCudaTensor_data(state, T), &v,
+                                                        (flags & VOLSTN_BWD_ONLY_GRID) ? NULL : &gv, THCudaTensor_data(state, gradT),
+                                                        &go, aligned, bytes, flags, (void *)THCState_getCurrentStream(state)));
+  return 1;
+}
+
 static const struct luaL_Reg cunn_BilinearSamplerVolumetric__[] = {
     {"BilinearSamplerVolumetric_updateOutput", cunn_BilinearSamplerVolumetric_updateOutput},
     {"BilinearSamplerVolumetric_updateGradInput", cunn_BilinearSamplerVolumetric_updateGradInput},
@@ -277,6 +327,8 @@ static const struct luaL_Reg cunn_BilinearSamplerVolumetric__[] = {
     {"CageWarpVolumetric_updateOutput", cunn_CageWarpVolumetric_updateOutput},
     {"CageWarpVolumetric_updateGradInput", cunn_CageWarpVolumetric_updateGradInput},
     {"CageWarpSmoothL1Volumetric_forwardBackward", cunn_CageWarpSmoothL1Volumetric_forwardBackward},
+    {"AffineSamplerVolumetric_updateOutput", cunn_AffineSamplerVolumetric_updateOutput},
+    {"AffineSamplerVolumetric_updateGradInput", cunn_AffineSamplerVolumetric_updateGradInput},
     {NULL, NULL}};
 
 static void cunn_BilinearSamplerVolumetric_init(lua_State *L) { /* …cu:1083-1088 */

@@ -11,6 +11,7 @@ end
 require('volstn.VolumetricGridGenerator')
 require('volstn.BilinearSamplerVolumetric')
 require('volstn.Cumsum')
+require('volstn.AffineSamplerVolumetric')           -- grid generator + sampler in one call (FloatTensor and CudaTensor)
 if withCuda then
    require('volstn.CageWarpVolumetric')            -- fused modules (CudaTensor only; INTEGRATION.md section 3)
    require('volstn.CageWarpSmoothL1Volumetric')

@@ -25,6 +25,8 @@ NEW_NAMES = ["Cumsum_updateOutput", "Cumsum_updateGradInput",
 # the fused modules of ALIGNet's warp head (lua/CageWarpVolumetric.lua, lua/CageWarpSmoothL1Volumetric.lua): CudaTensor only
 FUSED_NAMES = ["CageWarpVolumetric_updateOutput", "CageWarpVolumetric_updateGradInput",
                "CageWarpSmoothL1Volumetric_forwardBackward"]
+# lua/AffineSamplerVolumetric.lua: torch.FloatTensor (host, staged through the GPU) and torch.CudaTensor
+AFFINE_NAMES = ["AffineSamplerVolumetric_updateOutput", "AffineSamplerVolumetric_updateGradInput"]
 
 
 class _THTensor(ctypes.Structure):  # layout of HARNESS_DECLARE_TENSOR in include/TH.h

@@ -239,3 +239,43 @@ def test_fused_cage_warp_functions(libs):
         cuda.call("CageWarpVolumetric_updateOutput", ts, tc[:, :2].contiguous(), torch.empty((B, *oshape, 1), device="cuda"))
     with pytest.raises(luat.LuaError, match="stats must be"):
         cuda.call("CageWarpSmoothL1Volumetric_forwardBackward", ts, tc, tt, empty, empty, gcs, ws, np.zeros((B, 2)), 1.0, ZERO | ONLY_GRID)
+
+
+def test_affine_sampler_functions(libs):
+    """lua/AffineSamplerVolumetric.lua: the grid generator folded into the sampler, on torch.FloatTensor (lua/init.c, host
+    tensors staged through the GPU) and torch.CudaTensor (lua/init.cu) -- `output` has the bits of generator + sampler,
+    gradInputImages <= 1e-4, gradT <= 2e-5 of the oracle chain."""
+    from tests.test_gpu_rowwarp import random_affine
+    ours, cuda, _ = libs
+    rng = np.random.default_rng(29)
+    B, C, ishape, oshape = 5, 2, (7, 8, 9), (6, 9, 34)
+    vol = synth.volume("v1", B, *ishape, C, rng)
+    T = random_affine(B, rng)
+    go = synth.grad_output(B, *oshape, C, rng)
+    grid = np.empty((B, *oshape, 4), np.float32)
+    assert ours.call("VolumetricGridGenerator_updateOutput", T, grid) == 1          # the generator's own output on this library
+    ref_out = oracle.sampler_forward(vol, grid)
+    ref_gv, ref_gg = oracle.sampler_backward(vol, grid, go)
+    ref_gT = oracle.gridgen_backward(ref_gg)
+    # host tensors
+    out, gv, gT = np.full((B, *oshape, C), 7, np.float32), np.full_like(vol, 7), np.full_like(T, 7)
+    assert ours.call("AffineSamplerVolumetric_updateOutput", vol, T, out) == 1
+    assert bits_equal(out, ref_out)
+    assert ours.call("AffineSamplerVolumetric_updateGradInput", vol, T, gv, gT, go, _abi.BWD_ZERO_GRADVOL) == 1
+    assert max_rel(gv, ref_gv) <= 1e-4 and max_rel(gT, ref_gT) <= 2e-5
+    with pytest.raises(luat.LuaError, match="nil value"):                              # float only: not registered for Double
+        ours.call("AffineSamplerVolumetric_updateOutput", vol.astype(np.float64), T.astype(np.float64), out.astype(np.float64))
+    # CudaTensors; the backward's workspace tensor is module-owned and resized by the function
+    tv, tT, tgo = (torch.from_numpy(x).cuda() for x in (vol, T, go))
+    tout, tgv, tgT = torch.full((B, *oshape, C), 7.0, device="cuda"), torch.full_like(tv, 7.0), torch.full_like(tT, 7.0)
+    ws = luat.Tensor(torch.empty(1 << 18, device="cuda"))
+    assert cuda.call("AffineSamplerVolumetric_updateOutput", tv, tT, tout) == 1
+    assert bits_equal(tout.cpu().numpy(), ref_out)
+    assert cuda.call("AffineSamplerVolumetric_updateGradInput", tv, tT, tgv, tgT, tgo, ws, _abi.BWD_ZERO_GRADVOL) == 1
+    assert max_rel(tgv.cpu().numpy(), ref_gv) <= 1e-4 and max_rel(tgT.cpu().numpy(), ref_gT) <= 2e-5
+    empty = torch.empty(0, device="cuda")
+    tgT2 = torch.full_like(tT, 3.0)
+    assert cuda.call("AffineSamplerVolumetric_updateGradInput", tv, tT, empty, tgT2, tgo, ws, _abi.BWD_ZERO_GRADVOL | _abi.BWD_ONLY_GRID) == 1
+    assert max_rel(tgT2.cpu().numpy(), ref_gT) <= 2e-5
+    with pytest.raises(luat.LuaError, match="affine transform matrices"):
+        cuda.call("AffineSamplerVolumetric_updateOutput", tv, tT[:, :3].contiguous(), tout)

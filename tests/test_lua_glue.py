@@ -35,7 +35,8 @@ def test_luaopen_libvolstn_registers_the_reference_names(built):
     for tname in ("torch.FloatTensor", "torch.DoubleTensor"):   # init.c:18-19
         names = [n for t, _, n in regs if t == tname]
         assert names[:4] == luat.REFERENCE_NAMES                 # generic/...c:831-836, same order
-        assert names[4:] == luat.NEW_NAMES
+        assert names[4:8] == luat.NEW_NAMES
+        assert names[8:] == (luat.AFFINE_NAMES if tname == "torch.FloatTensor" else [])   # the fused host module is float only
     assert {t for t, _, _ in regs} == {"torch.FloatTensor", "torch.DoubleTensor"}
     h.close()
 
@@ -44,10 +45,10 @@ def test_luaopen_libcuvolstn_registers_the_reference_names(built):
     h = luat.Harness(luat.DROPIN_CUDA)
     assert h.opened == 1 and h.stack_after_open == 1             # init.cu:12-14
     regs = h.registrations()
-    assert [t for t, _, _ in regs] == ["torch.CudaTensor"] * 11  # ...cu:1083-1088
+    assert [t for t, _, _ in regs] == ["torch.CudaTensor"] * 13  # ...cu:1083-1088
     assert [n for _, _, n in regs][:4] == luat.REFERENCE_NAMES   # ...cu:1074-1080 (the OnlyGrid line is commented out there)
     assert [n for _, _, n in regs][4:8] == luat.NEW_NAMES
-    assert [n for _, _, n in regs][8:] == luat.FUSED_NAMES
+    assert [n for _, _, n in regs][8:] == luat.FUSED_NAMES + luat.AFFINE_NAMES
     h.close()
 
 
