@@ -265,6 +265,63 @@ static int cunn_CageWarpSmoothL1Volumetric_forwardBackward(lua_State *L) {
   return 1;
 }
 
+/* nn.BilinearSamplerSmoothL1Volumetric: (self, inputImages, grids, target, output, gradInputImages, gradGrids, workspace, stats,
+ * gradScale [, flags]) -- the training step around a plain sampler (a network that emits a dense field): forward, SmoothL1 and
+ * its gradient, IoU counts and the backward in one kernel; gradGrids has the bits of the module chain.  Buffers and the
+ * synchronisation as for nn.CageWarpSmoothL1Volumetric above. */
+static int cunn_BilinearSamplerSmoothL1Volumetric_forwardBackward(lua_State *L) {
+  THCState *state = volstn_cutorch_state(L);
+  THCudaTensor *inputImages = (THCudaTensor *)luaT_checkudata(L, 2, "torch.CudaTensor");
+  THCudaTensor *grids = (THCudaTensor *)luaT_checkudata(L, 3, "torch.CudaTensor");
+  THCudaTensor *target = (THCudaTensor *)luaT_checkudata(L, 4, "torch.CudaTensor");
+  THCudaTensor *output = (THCudaTensor *)luaT_checkudata(L, 5, "torch.CudaTensor");
+  THCudaTensor *gradInputImages = (THCudaTensor *)luaT_checkudata(L, 6, "torch.CudaTensor");
+  THCudaTensor *gradGrids = (THCudaTensor *)luaT_checkudata(L, 7, "torch.CudaTensor");
+  THCudaTensor *workspace = (THCudaTensor *)luaT_checkudata(L, 8, "torch.CudaTensor");
+  THDoubleTensor *stats = (THDoubleTensor *)luaT_checkudata(L, 9, "torch.DoubleTensor");
+  const float grad_scale = (float)lua_tonumber(L, 10);
+  const unsigned flags = volstn_glue_flags(lua_tonumber(L, 11));
+  cudaStream_t st = (cudaStream_t)THCState_getCurrentStream(state);
+  volstn_tensor5 v, g, t, o, gv, gg;
+  long B, b;
+  const int keep = THCudaTensor_nElement(state, output) > 0;
+  char *ws;
+  double *loss, *host;
+  uint64_t *iou;
+  cunn_volstn_desc5(state, &v, inputImages, "inputImages");
+  cunn_volstn_desc5(state, &g, grids, "grids");
+  cunn_volstn_desc5(state, &t, target, "target");
+  cunn_volstn_desc5(state, &gg, gradGrids, "gradGrids");
+  B = THCudaTensor_size(state, inputImages, 0);
+  if (keep) cunn_volstn_desc5(state, &o, output, "output");
+  if (!(flags & VOLSTN_BWD_ONLY_GRID)) cunn_volstn_desc5(state, &gv, gradInputImages, "gradInputImages");
+  if (THDoubleTensor_nDimension(stats) != 2 || THDoubleTensor_size(stats, 0) != B || THDoubleTensor_size(stats, 1) != 3 ||
+      !THDoubleTensor_isContiguous(stats))
+    THError("nn.BilinearSamplerSmoothL1Volumetric: stats must be a contiguous B x 3 torch.DoubleTensor");
+  THCudaTensor_resize1d(state, workspace, 6 * B + 2);
+  ws = (char *)(((size_t)THCudaTensor_data(state, workspace) + 7) & ~(size_t)7);
+  loss = (double *)ws;
+  iou = (uint64_t *)(ws + 8 * (size_t)B);
+  VOLSTN_GLUE_CHECK("BilinearSamplerSmoothL1Volumetric.forwardBackward",
+                    volstn_b200_sampler_step(VOLSTN_F32, (int)g.size[4], &v, &g, &t, keep ? &o : NULL,
+                                             (flags & VOLSTN_BWD_ONLY_GRID) ? NULL : &gv, &gg, loss, iou, grad_scale, flags, (void *)st));
+  host = (double *)malloc(24 * (size_t)(B > 0 ? B : 1));
+  if (!host) THError("nn.BilinearSamplerSmoothL1Volumetric: out of memory");
+  if (cudaMemcpyAsync(host, ws, 24 * (size_t)B, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    free(host);
+    THError("nn.BilinearSamplerSmoothL1Volumetric: reading the loss back failed");
+  }
+  for (b = 0; b < B; b++) {
+    double *row = THDoubleTensor_data(stats) + 3 * b;
+    const uint64_t *cnt = (const uint64_t *)(host + B) + 2 * b;
+    row[0] = host[b];
+    row[1] = (double)cnt[0];
+    row[2] = (double)cnt[1];
+  }
+  free(host);
+  return 1;
+}
+
 /* nn.AffineSamplerVolumetric on CudaTensors: (self, inputImages, T, output [, flags]) /
  * (self, inputImages, T, gradInputImages, gradT, gradOutput, workspace [, flags]); `workspace` is a module-owned CudaTensor
  * that is resized here (partial sums of the deterministic gradT reduction). */
@@ -327,6 +384,7 @@ static const struct luaL_Reg cunn_BilinearSamplerVolumetric__[] = {
     {"CageWarpVolumetric_updateOutput", cunn_CageWarpVolumetric_updateOutput},
     {"CageWarpVolumetric_updateGradInput", cunn_CageWarpVolumetric_updateGradInput},
     {"CageWarpSmoothL1Volumetric_forwardBackward", cunn_CageWarpSmoothL1Volumetric_forwardBackward},
+    {"BilinearSamplerSmoothL1Volumetric_forwardBackward", cunn_BilinearSamplerSmoothL1Volumetric_forwardBackward},
     {"AffineSamplerVolumetric_updateOutput", cunn_AffineSamplerVolumetric_updateOutput},
     {"AffineSamplerVolumetric_updateGradInput", cunn_AffineSamplerVolumetric_updateGradInput},
     {NULL, NULL}};

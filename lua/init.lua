@@ -15,6 +15,7 @@ require('volstn.AffineSamplerVolumetric')           -- grid generator + sampler 
 if withCuda then
    require('volstn.CageWarpVolumetric')            -- fused modules (CudaTensor only; INTEGRATION.md section 3)
    require('volstn.CageWarpSmoothL1Volumetric')
+   require('volstn.BilinearSamplerSmoothL1Volumetric')
 end
 
 return nn

@@ -24,7 +24,7 @@ NEW_NAMES = ["Cumsum_updateOutput", "Cumsum_updateGradInput",
              "VolumetricGridGenerator_updateOutput", "VolumetricGridGenerator_updateGradInput"]
 # the fused modules of ALIGNet's warp head (lua/CageWarpVolumetric.lua, lua/CageWarpSmoothL1Volumetric.lua): CudaTensor only
 FUSED_NAMES = ["CageWarpVolumetric_updateOutput", "CageWarpVolumetric_updateGradInput",
-               "CageWarpSmoothL1Volumetric_forwardBackward"]
+               "CageWarpSmoothL1Volumetric_forwardBackward", "BilinearSamplerSmoothL1Volumetric_forwardBackward"]
 # lua/AffineSamplerVolumetric.lua: torch.FloatTensor (host, staged through the GPU) and torch.CudaTensor
 AFFINE_NAMES = ["AffineSamplerVolumetric_updateOutput", "AffineSamplerVolumetric_updateGradInput"]
 

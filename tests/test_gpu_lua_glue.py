@@ -279,3 +279,29 @@ def test_affine_sampler_functions(libs):
     assert max_rel(tgT2.cpu().numpy(), ref_gT) <= 2e-5
     with pytest.raises(luat.LuaError, match="affine transform matrices"):
         cuda.call("AffineSamplerVolumetric_updateOutput", tv, tT[:, :3].contiguous(), tout)
+
+
+def test_sampler_smooth_l1_step_function(libs):
+    """lua/BilinearSamplerSmoothL1Volumetric.lua: the one-kernel step with a grid tensor through the fake stack -- forward bits,
+    loss, exact IoU counts, gradGrids bit-exact against the oracle fed with the criterion's gradient (G = 4 and 3)."""
+    _, cuda, _ = libs
+    rng = np.random.default_rng(37)
+    B, ishape, oshape = 3, (8, 9, 11), (6, 9, 20)
+    vol = synth.volume("v2", B, *ishape, 1, rng)
+    tgt = synth.volume("v2", B, *oshape, 1, rng)
+    for G in (4, 3):
+        grid = synth.grid("g2", B, *oshape, rng, G=G, csz=4)
+        ref_out = oracle.sampler_forward(vol, grid, G)
+        ref_gv, ref_gg = oracle.sampler_backward(vol, grid, oracle.smooth_l1_backward(ref_out, tgt), G)
+        n = int(np.prod(tgt.shape))
+        tv, tg, tt = (torch.from_numpy(x).cuda() for x in (vol, grid, tgt))
+        kept, gv, gg = torch.full((B, *oshape, 1), 9.0, device="cuda"), torch.full_like(tv, 9.0), torch.full_like(tg, 9.0)
+        stats = np.full((B, 3), -1.0)
+        ws = luat.Tensor(torch.empty(64, device="cuda"))
+        scale = float(np.float32(1.0 / np.float32(n)))
+        assert cuda.call("BilinearSamplerSmoothL1Volumetric_forwardBackward", tv, tg, tt, kept, gv, gg, ws, stats, scale,
+                         _abi.BWD_ZERO_GRADVOL) == 1
+        assert bits_equal(kept.cpu().numpy(), ref_out) and bits_equal(gg.cpu().numpy(), ref_gg), G
+        assert max_rel(gv.cpu().numpy(), ref_gv) <= 1e-4
+        assert abs(stats[:, 0].sum() / n - oracle.smooth_l1_forward(ref_out, tgt)) <= 1e-9
+        assert np.array_equal(stats[:, 1:].astype(np.uint64), oracle.iou_counts(ref_out, tgt))

@@ -45,7 +45,7 @@ def test_luaopen_libcuvolstn_registers_the_reference_names(built):
     h = luat.Harness(luat.DROPIN_CUDA)
     assert h.opened == 1 and h.stack_after_open == 1             # init.cu:12-14
     regs = h.registrations()
-    assert [t for t, _, _ in regs] == ["torch.CudaTensor"] * 13  # ...cu:1083-1088
+    assert [t for t, _, _ in regs] == ["torch.CudaTensor"] * 14  # ...cu:1083-1088
     assert [n for _, _, n in regs][:4] == luat.REFERENCE_NAMES   # ...cu:1074-1080 (the OnlyGrid line is commented out there)
     assert [n for _, _, n in regs][4:8] == luat.NEW_NAMES
     assert [n for _, _, n in regs][8:] == luat.FUSED_NAMES + luat.AFFINE_NAMES
