@@ -127,3 +127,63 @@ def test_lua_files_call_only_registered_functions(built):
     # and nothing registered is orphaned except the G = 3 twins, which the reference registers and never wraps
     orphans = (reg_cuda | reg_float) - set(called)
     assert orphans == {"BilinearSamplerBHWD_updateOutput", "BilinearSamplerBHWD_updateGradInput"}, orphans
+
+
+def test_lua_call_sites_match_the_stack_slots_the_c_functions_read():
+    """Static: the number of arguments at every `x.nn.<Name>(self, ...)` call site of lua/*.lua against the highest stack slot
+    the registered C function reads (luaT_checkudata / lua_tonumber).  The last slot of every function is the optional flags
+    number (nil reads as 0), so a call may pass one argument fewer."""
+    import glob
+    import re
+
+    def strip_lua(src):
+        src = re.sub(r"--\[\[.*?\]\]", "", src, flags=re.S)
+        return "\n".join(l.split("--")[0] for l in src.splitlines())
+
+    def call_args(src, start):              # arguments of the call whose '(' is at `start`
+        depth, n, i = 0, 1, start
+        while True:
+            c = src[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n
+            elif c == "," and depth == 1:
+                n += 1
+            i += 1
+
+    csrc = open(os.path.join(luat.ROOT, "lua", "init.cu")).read() + open(os.path.join(luat.ROOT, "lua", "generic", "volstn_host.c")).read()
+
+    def bodies(fname):                      # bodies of `static int cunn_<fname>(lua_State *L...)` / `nn_(<fname>)(...)`, brace-matched
+        out = []
+        for m in re.finditer(r"static int (?:cunn_" + fname + r"|nn_\(" + fname + r"\))\(lua_State \*L[^)]*\) \{", csrc):
+            depth, i = 1, m.end()
+            while depth:
+                depth += {"{": 1, "}": -1}.get(csrc[i], 0)
+                i += 1
+            out.append(csrc[m.end():i])
+        return out
+
+    def max_slot(name):
+        slots = []
+        for body in bodies(name):
+            for helper in re.findall(r"return (?:cunn_|nn_\()(volstn_[A-Za-z_]+)\)?\(L", body):      # thin wrappers (sampler, cumsum)
+                body += "".join(bodies(helper))
+            slots.append(max(int(x) for x in re.findall(r"(?:luaT_checkudata|lua_tonumber)\(L, (\d+)", body)))
+        assert slots, name
+        return slots
+
+    checked = 0
+    for path in glob.glob(os.path.join(luat.ROOT, "lua", "*.lua")):
+        src = strip_lua(open(path).read())
+        for m in re.finditer(r"\.nn\.([A-Za-z0-9_]+)\(", src):
+            nargs = call_args(src, m.end() - 1)
+            for top in max_slot(m.group(1)):
+                if nargs in (top, top - 1):
+                    break
+            else:
+                raise AssertionError((os.path.basename(path), m.group(1), nargs, max_slot(m.group(1))))
+            checked += 1
+    assert checked >= 14, checked
