@@ -37,6 +37,7 @@ end
 function Affine:updateOutput(input)
    self:check(input)
    local images, T = input[1], input[2]:contiguous()
+   if torch.type(self.output) ~= torch.type(images) then self.output = images.new() end
    self.output:resize(images:size(1), self.depth, self.height, self.width, images:size(5))
    images.nn.AffineSamplerVolumetric_updateOutput(self, images, T, self.output)
    return self.output

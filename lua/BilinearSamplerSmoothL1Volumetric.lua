@@ -33,7 +33,10 @@ function Step:forwardBackward(input, target)
    self.gradInput[1] = self.gradInput[1] or images.new()
    self.gradInput[2] = (self.gradInput[2] or images.new()):resizeAs(grids)
    if self.onlyGrid then self.gradInput[1]:resize(0) else self.gradInput[1]:resizeAs(images) end
+   if torch.type(self.output) ~= torch.type(images) then self.output = images.new() end
    if self.keepOutput then self.output:resizeAs(target) else self.output:resize(0) end
+   -- nn.Module:type() (model:cuda()) converts every tensor field: `stats` must stay a HOST DoubleTensor, `output` follows the input
+   if torch.type(self.stats) ~= 'torch.DoubleTensor' then self.stats = torch.DoubleTensor() end
    self.stats:resize(B, 3)
    local flags = ZERO_GRADVOL + (self.onlyGrid and ONLY_GRID or 0)
    local gradScale = self.sizeAverage and (1 / n) or 1

@@ -36,7 +36,10 @@ function Step:forwardBackward(input, target)
    self.gradInput[1] = self.gradInput[1] or source.new()
    self.gradInput[2] = (self.gradInput[2] or source.new()):resizeAs(cage)
    if self.onlyGrid then self.gradInput[1]:resize(0) else self.gradInput[1]:resizeAs(source) end
+   if torch.type(self.output) ~= torch.type(source) then self.output = source.new() end
    if self.keepOutput then self.output:resizeAs(target) else self.output:resize(0) end
+   -- nn.Module:type() (model:cuda()) converts every tensor field: `stats` must stay a HOST DoubleTensor, `output` follows the input
+   if torch.type(self.stats) ~= 'torch.DoubleTensor' then self.stats = torch.DoubleTensor() end
    self.stats:resize(B, 3)
    local flags = ZERO_GRADVOL + (self.onlyGrid and ONLY_GRID or 0) + (self.fastArith and FAST_ARITH or 0)
    local gradScale = self.sizeAverage and (1 / n) or 1                 -- THNN: norm = sizeAverage ? 1. / nElement : 1.

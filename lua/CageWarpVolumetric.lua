@@ -49,6 +49,7 @@ end
 function CageWarp:updateOutput(input)
    self:check(input)
    local source, cage = input[1], input[2]
+   if torch.type(self.output) ~= torch.type(source) then self.output = source.new() end
    self.output:resize(source:size(1), self.depth or source:size(2), self.height or source:size(3),
                       self.width or source:size(4), source:size(5))
    source.nn.CageWarpVolumetric_updateOutput(self, source, cage, self.output, self:flags())
