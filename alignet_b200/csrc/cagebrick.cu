@@ -119,10 +119,11 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
         const float o = fmaf(fz, dzv, g0);
         const float x = o - tg[r];
         // THNN SmoothL1Criterion: z = |x|; loss += z < 1 ? 0.5 z^2 : z - 0.5; gradient norm * clamp(x, -1, 1)
-        go = a.loss_norm * fminf(fmaxf(x, -1.0f), 1.0f);
+        const float cl = fminf(fmaxf(x, -1.0f), 1.0f);
+        go = a.loss_norm * cl;
         if (valid) {
-          const float zz = fabsf(x);
-          L.lsum += zz < 1.0f ? 0.5f * zz * zz : zz - 0.5f;
+          // z < 1 ? 0.5 z^2 : z - 0.5  ==  cl . (x - 0.5 cl)  with cl = clamp(x, -1, 1): two FMAs instead of a branchy seven
+          L.lsum = fmaf(cl, fmaf(-0.5f, cl, x), L.lsum);
           const bool p = o > 0.5f, q = tg[r] > 0.5f;  // computeIOU (util.lua:110-120)
           L.ni += (p & q) ? 1 : 0;
           L.nu += (p | q) ? 1 : 0;
