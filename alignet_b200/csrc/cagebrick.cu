@@ -52,8 +52,8 @@ struct BrickLane {
 template <int MODE, bool GV, int NR, int TIER>
 __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__restrict__ vb, const float (&c)[NR][3],
                                            const float (&wyh)[NR], const float (&tg)[NR], const float *__restrict__ tp,
-                                           float *__restrict__ op, bool valid, BrickLane &L) {
-  const int sH = a.iW, sD = a.iH * a.iW;
+                                           float *__restrict__ op, bool keep, bool valid, BrickLane &L) {
+  const int sH = a.iW, sD = a.sD;
   float f[NR][3];
   const float *p0[NR];
   bool zl[NR], zh[NR], yl[NR], yh[NR], xl[NR], xh[NR];
@@ -116,23 +116,21 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
     } else {
       float go;
       if constexpr (MODE == 2) {
-        const float o = fmaf(fz, dzv, g0);
+        // a lane beyond the row (ragged last x slot) carries out = target = 0: every term below vanishes without a branch
+        const float o = valid ? fmaf(fz, dzv, g0) : 0.0f;
         const float x = o - tg[r];
         // THNN SmoothL1Criterion: z = |x|; loss += z < 1 ? 0.5 z^2 : z - 0.5; gradient norm * clamp(x, -1, 1)
         const float cl = fminf(fmaxf(x, -1.0f), 1.0f);
         go = a.loss_norm * cl;
-        if (valid) {
-          // z < 1 ? 0.5 z^2 : z - 0.5  ==  cl . (x - 0.5 cl)  with cl = clamp(x, -1, 1): two FMAs instead of a branchy seven
-          L.lsum = fmaf(cl, fmaf(-0.5f, cl, x), L.lsum);
-          const bool p = o > 0.5f, q = tg[r] > 0.5f;  // computeIOU (util.lua:110-120)
-          L.ni += (p & q) ? 1 : 0;
-          L.nu += (p | q) ? 1 : 0;
-          if (op) st_stream_f1(op + r * a.oW, o);
-        }
+        // z < 1 ? 0.5 z^2 : z - 0.5  ==  cl . (x - 0.5 cl)  with cl = clamp(x, -1, 1): two FMAs instead of a branchy seven
+        L.lsum = fmaf(cl, fmaf(-0.5f, cl, x), L.lsum);
+        const bool p = o > 0.5f, q = tg[r] > 0.5f;  // computeIOU (util.lua:110-120)
+        L.ni += (p & q) ? 1 : 0;
+        L.nu += (p | q) ? 1 : 0;
+        if (keep && valid) st_stream_f1(op + r * a.oW, o);
       } else {
-        go = tg[r];
+        go = valid ? tg[r] : 0.0f;
       }
-      if (!valid) go = 0.0f;
       // d out / d coordinate (voxel units): z: dzv; y: lerp_z of the y differences; x: lerp_z lerp_y of the x differences
       const float dyv = fmaf(fz, dy1 - dy0, dy0);
       const float hx0 = fmaf(fy, dx1 - dx0, dx0), hx1 = fmaf(fy, dx3 - dx2, dx2);
@@ -162,28 +160,35 @@ __device__ __forceinline__ void brick_body(const BrickArgs &a, const float *__re
 template <int MODE, bool GV, int NR>
 __device__ __forceinline__ void brick_rows(const BrickArgs &a, const float *__restrict__ vb, const float (&C0)[3],
                                            const float (&D)[3], const float (&wyh)[NR], const float *__restrict__ tp,
-                                           float *__restrict__ op, bool valid, BrickLane &L) {
+                                           float *__restrict__ op, bool keep, bool valid, BrickLane &L) {
   float c[NR][3], tg[NR];
-  bool strict = true, inside = true;
+  unsigned u[NR][3];
+  bool strict = true;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
 #pragma unroll
     for (int i = 0; i < 3; i++) c[r][i] = fmaf(wyh[r], D[i], C0[i]);
     // strict: -eps <= c < size - 1 on every axis, inside: -eps <= c < size - eps: unsigned compares on the IEEE bits of
     // c + eps (negative and NaN patterns are larger than any positive bound)
-    const unsigned uz = (unsigned)__float_as_int(c[r][0] + a.ez), uy = (unsigned)__float_as_int(c[r][1] + a.ey),
-                   ux = (unsigned)__float_as_int(c[r][2] + a.ex);
-    strict = strict & (uz < a.ubz) & (uy < a.uby) & (ux < a.ubx);
-    inside = inside & (uz < a.uiz) & (uy < a.uiy) & (ux < a.uix);
+    u[r][0] = (unsigned)__float_as_int(c[r][0] + a.ez), u[r][1] = (unsigned)__float_as_int(c[r][1] + a.ey);
+    u[r][2] = (unsigned)__float_as_int(c[r][2] + a.ex);
+    strict = strict & (u[r][0] < a.ubz) & (u[r][1] < a.uby) & (u[r][2] < a.ubx);
     tg[r] = 0.0f;
-    if constexpr (MODE != 0) tg[r] = ld_stream_f1(tp + r * a.oW);
+    if constexpr (MODE != 0) {
+      if (valid) tg[r] = ld_stream_f1(tp + r * a.oW);
+    }
   }
-  if (__all_sync(0xffffffffu, strict))
-    brick_body<MODE, GV, NR, 0>(a, vb, c, wyh, tg, tp, op, valid, L);
-  else if (__all_sync(0xffffffffu, inside))
-    brick_body<MODE, GV, NR, 1>(a, vb, c, wyh, tg, tp, op, valid, L);
+  if (__all_sync(0xffffffffu, strict)) {
+    brick_body<MODE, GV, NR, 0>(a, vb, c, wyh, tg, tp, op, keep, valid, L);
+    return;
+  }
+  bool inside = true;  // only the trips that are not strict pay for the second test
+#pragma unroll
+  for (int r = 0; r < NR; r++) inside = inside & (u[r][0] < a.uiz) & (u[r][1] < a.uiy) & (u[r][2] < a.uix);
+  if (__all_sync(0xffffffffu, inside))
+    brick_body<MODE, GV, NR, 1>(a, vb, c, wyh, tg, tp, op, keep, valid, L);
   else
-    brick_body<MODE, GV, NR, 2>(a, vb, c, wyh, tg, tp, op, valid, L);
+    brick_body<MODE, GV, NR, 2>(a, vb, c, wyh, tg, tp, op, keep, valid, L);
 }
 
 #ifndef BRICK_MIN_CTAS
@@ -261,7 +266,8 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
   const float *vb = opaque(a.vol + (long long)b * a.vB);
   const long long osample = (long long)a.oD * a.oH * a.oW;  // < 2^31: in-sample element offsets are 32-bit
   const float *tb = (MODE != 0) ? opaque(a.tgt + (long long)b * osample + xc) : nullptr;
-  float *ob = a.out ? opaque(a.out + (long long)b * osample + xc) : nullptr;
+  const bool keep = a.out != nullptr;  // uniform: the forward value is stored (always in the forward kernel, on request in the step)
+  float *ob = opaque(a.out + (keep ? (long long)b * osample + xc : 0));
 
   for (int z = za; z < zb; z++) {
     const float2 wz = m.wz[z];
@@ -282,11 +288,11 @@ __global__ void __launch_bounds__(kBrickThreads, BRICK_MIN_CTAS) k_cage_brick(co
       float wyh[NRT];
 #pragma unroll
       for (int r = 0; r < NRT; r++) wyh[r] = m.wy[y + r].y;
-      brick_rows<MODE, GV, NRT>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, NRT>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob + eo, keep, valid, L);
     }
     for (; y < yb; y++, eo += a.oW) {
       const float wyh[1] = {m.wy[y].y};
-      brick_rows<MODE, GV, 1>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob ? ob + eo : nullptr, valid, L);
+      brick_rows<MODE, GV, 1>(a, vb, C0, D, wyh, MODE != 0 ? tb + eo : nullptr, ob + eo, keep, valid, L);
     }
     if constexpr (MODE != 0) {
       // c = C0 + wy_hi (C1 - C0): d/dC1 = T1, d/dC0 = T0 - T1; C_j = F_j h + h and F_j = P_j0 + wz_hi (P_j1 - P_j0)
@@ -387,6 +393,7 @@ void brick_plan(BrickArgs &a) {
     if (v >= 1 && v <= 64) a.ysplit = v;
   }
   a.ntask = a.nzu * a.zsplit * a.nyu * a.ysplit * a.nxs;
+  a.sD = a.iH * a.iW;
   const float dm1 = (float)(a.iD - 1), hm1 = (float)(a.iH - 1), wm1 = (float)(a.iW - 1);
   a.hz2 = dm1 * 0.5f, a.hy2 = hm1 * 0.5f, a.hx2 = wm1 * 0.5f;
   memcpy(&a.fbz, &dm1, 4), memcpy(&a.fby, &hm1, 4), memcpy(&a.fbx, &wm1, 4);

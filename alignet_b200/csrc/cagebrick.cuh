@@ -17,6 +17,7 @@ struct BrickArgs {
   int B, iD, iH, iW, oD, oH, oW, cD, cH, cW;
   // plan (brick_plan)
   int nzu, nyu, nxs, zsplit, ysplit, ntask;
+  int sD;                     // iH * iW: elements per source plane
   float hz2, hy2, hx2;        // (size - 1) / 2 per source axis
   unsigned fbz, fby, fbx;     // IEEE bits of (float)(size - 1): the strict-tier test
   float cmz, cmy, cmx;        // size + 1: upper clamp of the general tier
