@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from alignet_b200 import nn as vnn, synth
+from alignet_b200 import _abi, nn as vnn, synth
 from oracle import oracle
 from tests._util import bits_equal, max_rel
 
@@ -285,3 +285,38 @@ def test_host_calls_from_concurrent_threads():
         assert max_rel(gv, rgv) <= 1e-4, i
         agrid = vnn.VolumetricGridGenerator(*vol.shape[1:4]).updateOutput(torch.from_numpy(T).cuda()).cpu().numpy()
         assert bits_equal(aff, oracle.sampler_forward(vol, agrid)), i
+
+
+def test_host_pin_unpin_contexts_and_error_reporting():
+    """The housekeeping entry points of the host ABI: pin / unpin of caller-owned buffers (cudaHostRegister: optional, the
+    results must not depend on it), explicit contexts (create / destroy, more than one alive), placement queries, and the
+    per-thread CUDA error record behind VOLSTN_ERR_CUDA."""
+    import ctypes
+    lib = _abi.lib()
+    rng = np.random.default_rng(9)
+    B, N, C = 5, 12, 2
+    vol = synth.volume("v1", B, N, N, N, C, rng)
+    grid = synth.grid("g2", B, N, N, N, rng, csz=4)
+    ref = oracle.sampler_forward(vol, grid)
+    ctxs = [ctypes.c_void_p() for _ in range(2)]
+    for c in ctxs:
+        assert lib.volstn_b200_host_ctx_create(0, ctypes.byref(c)) == 0 and c.value
+    out_plain, out_pinned = np.empty_like(ref), np.empty_like(ref)
+    d = vnn._desc
+    tv, tg = torch.from_numpy(vol), torch.from_numpy(grid)
+    assert lib.volstn_b200_host_sampler_forward(ctxs[0], 0, 4, d(tv), d(tg), d(torch.from_numpy(out_plain)), 0) == 0
+    for a in (vol, grid, out_pinned):
+        assert lib.volstn_b200_host_pin(ctypes.c_void_p(a.ctypes.data), ctypes.c_size_t(a.nbytes)) == 0
+    assert lib.volstn_b200_host_sampler_forward(ctxs[1], 0, 4, d(tv), d(tg), d(torch.from_numpy(out_pinned)), 0) == 0
+    for a in (vol, grid, out_pinned):
+        assert lib.volstn_b200_host_unpin(ctypes.c_void_p(a.ctypes.data)) == 0
+    assert bits_equal(out_plain, ref) and bits_equal(out_pinned, ref)
+    assert lib.volstn_b200_host_unpin(ctypes.c_void_p(vol.ctypes.data)) == _abi.ERR_CUDA          # not registered any more ...
+    assert lib.volstn_b200_last_cuda_error() != 0                                                   # ... and the record says why
+    assert len(lib.volstn_b200_last_cuda_error_string()) > 0
+    assert lib.volstn_b200_host_ctx_create(10 ** 6, ctypes.byref(ctypes.c_void_p())) != 0           # no such device
+    node = lib.volstn_b200_host_numa_node(0)
+    assert node >= -1
+    assert lib.volstn_b200_host_bind_thread(0) >= 0                                                 # a no-op without topology information
+    for c in ctxs:
+        assert lib.volstn_b200_host_ctx_destroy(c) == 0
