@@ -23,6 +23,9 @@ void set_last_cuda_error(cudaError_t e);           // abi.cu (thread local)
 
 inline int cuda_fail(cudaError_t e) {
   set_last_cuda_error(e);
+  // A failing runtime call also leaves its code in the runtime's per-thread "last error"; unless it is taken out here the
+  // NEXT launch's after_launch() would report this call's failure as its own (found by the test that unpins a buffer twice).
+  (void)cudaGetLastError();
   return VOLSTN_ERR_CUDA;
 }
 #define VOLSTN_CUDA_TRY(expr)                                   \
